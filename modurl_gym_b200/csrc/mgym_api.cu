@@ -1,0 +1,703 @@
+// mgym_api.cu -- C ABI (include/mgym.h) over the CUDA kernels.  No torch types, no CPU fallback.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+
+#include "../../include/mgym.h"
+#include "mgym_kernels.cuh"
+
+using namespace mgym;
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct mgym_env {
+  int kind = 0;
+  uint64_t n = 0;
+  int device = 0;
+  uint64_t seed = 0;
+  mgym_config cfg{};
+  int cnt_mode = CNT_NONE;
+  bool vec4 = false;  // n % 4 == 0 and env_index_base % 4 == 0
+
+  float* state = nullptr;
+  void* steps = nullptr;
+  uint32_t* sbt = nullptr;
+  float* ep_return = nullptr;
+  float* reset_pool = nullptr;
+  uint64_t pool_len = 0;
+  unsigned long long* stats = nullptr;  // 5 x 8 bytes
+  uint32_t* bad_action = nullptr;
+
+  uint64_t t = 0;         // steps executed since creation
+  uint64_t n_resets = 0;  // explicit reset calls since creation
+  EnvConsts k{};
+  int num_sms = 0;
+
+  // device staging for mgym_step_host
+  void* h_actions = nullptr;
+  float* h_obs = nullptr;
+  float* h_reward = nullptr;
+  uint8_t* h_flags = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define MGYM_CUDA(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? MGYM_ERR_OUT_OF_MEMORY : MGYM_ERR_CUDA,        \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+constexpr int kStateDim[MGYM_NUM_KINDS] = {4, 2, 2, 2, 4};
+constexpr int kObsDim[MGYM_NUM_KINDS] = {4, 2, 2, 3, 6};
+constexpr int kContinuous[MGYM_NUM_KINDS] = {0, 0, 1, 1, 0};
+constexpr int kNumActions[MGYM_NUM_KINDS] = {2, 3, 0, 0, 3};
+const char* const kNames[MGYM_NUM_KINDS] = {"CartPole-v1", "MountainCar-v0", "MountainCarContinuous-v0",
+                                            "Pendulum-v1", "Acrobot-v1"};
+
+bool valid_kind(int kind) { return kind >= 0 && kind < MGYM_NUM_KINDS; }
+size_t action_size(int kind) { return kContinuous[kind] ? sizeof(float) : sizeof(uint8_t); }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// f32 constants, evaluated in the constructors' operator order (cartpole.rs:45-56,
+// mountain_car.rs:35-40).  volatile keeps the host compiler from re-associating.
+EnvConsts make_consts(int kind, const mgym_config& cfg) {
+  EnvConsts k{};
+  volatile float masscart = 1.0f, masspole = 0.1f, length = 0.5f, tau = 0.02f;
+  k.gravity = 9.8f;
+  k.masspole = masspole;
+  k.total_mass = masspole + masscart;
+  k.length = length;
+  k.polemass_length = masspole * length;
+  k.force_mag = 10.0f;
+  k.tau = tau;
+  volatile float half_tau = 0.5f * tau;
+  k.half_tau = half_tau;
+  k.half_tau_tau = half_tau * tau;
+  volatile float th = 12.0f * 2.0f;
+  th = th * 3.14159274101257324f;  // std::f32::consts::PI
+  th = th / 360.0f;
+  k.theta_threshold = th;
+  k.x_threshold = 2.4f;
+  volatile float four = 4.0f, three = 3.0f;
+  k.four_thirds = four / three;
+
+  k.min_position = -1.2f;
+  k.max_position = 0.6f;
+  k.max_speed = 0.07f;
+  k.goal_position = 0.5f;
+  k.goal_velocity = cfg.goal_velocity;
+  k.force = 0.001f;
+  k.mc_gravity = 0.0025f;
+  k.power = 0.0015f;
+
+  volatile float m1 = 1.0f, m2 = 1.0f, l1 = 1.0f, lc1 = 0.5f, lc2 = 0.5f, g = 9.8f, dt = 0.2f;
+  volatile float a = m1 * lc1, b = m2 * l1;
+  volatile float ab = a + b;
+  k.m1lc1g = ab * g;
+  volatile float c = m2 * lc2;
+  k.m2lc2g = c * g;
+  k.dt = dt;
+  k.dt2 = dt / 2.0f;
+  k.dt6 = dt / 6.0f;
+  volatile float pi = PI_F;
+  k.max_vel_1 = 4.0f * pi;
+  k.max_vel_2 = 9.0f * pi;
+
+  k.is_euler = cfg.is_euler;
+  k.sutton_barto = cfg.sutton_barto_reward;
+  k.max_steps = (kind == MGYM_CARTPOLE_V1) ? 0 : cfg.max_episode_steps;
+  return k;
+}
+
+KernelParams base_params(const mgym_env* e) {
+  KernelParams p{};
+  p.state = e->state;
+  p.steps = e->steps;
+  p.sbt = e->sbt;
+  p.ep_return = e->ep_return;
+  p.reset_pool = e->pool_len ? e->reset_pool : nullptr;
+  p.pool_len = e->pool_len;
+  p.stats = (e->cfg.auto_reset && e->cfg.track_stats) ? e->stats : nullptr;
+  p.bad_action = e->cfg.validate_actions ? e->bad_action : nullptr;
+  p.n = e->n;
+  p.seed = e->seed;
+  p.env_base = e->cfg.env_index_base;
+  p.t = e->t;
+  p.k = e->k;
+  return p;
+}
+
+int env_blocks_per_sm() {
+  static int v = [] {
+    const char* s = getenv("MGYM_BLOCKS_PER_SM");
+    return s ? atoi(s) : 0;
+  }();
+  return v;
+}
+
+template <typename Kernel>
+int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, uint64_t groups, cudaStream_t st) {
+  constexpr int threads = 256;
+  int per_sm = 0;
+  MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
+  uint64_t blocks = (uint64_t)e->num_sms * per_sm;
+  const uint64_t need = (groups + threads - 1) / threads;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  kernel<<<(unsigned)blocks, threads, 0, st>>>(p);
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+// kind x vector width x auto/manual x counter width
+template <int KIND, int V, bool ROLLOUT>
+int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
+  const uint64_t groups = p.n / V;
+  const bool autor = e->cfg.auto_reset != 0;
+#define MGYM_LAUNCH(AUTO_, CNT_)                                                                         \
+  do {                                                                                                   \
+    if constexpr (ROLLOUT)                                                                               \
+      return launch_persistent(rollout_kernel<KIND, V, AUTO_, CNT_>, e, p, groups, st);                  \
+    else                                                                                                 \
+      return launch_persistent(step_kernel<KIND, V, AUTO_, CNT_>, e, p, groups, st);                     \
+  } while (0)
+  if (!autor) MGYM_LAUNCH(false, CNT_U32);
+  if constexpr (KIND == 0) {
+    MGYM_LAUNCH(true, CNT_U16);
+  } else {
+    switch (e->cnt_mode) {
+      case CNT_NONE: MGYM_LAUNCH(true, CNT_NONE);
+      case CNT_U16: MGYM_LAUNCH(true, CNT_U16);
+      default: MGYM_LAUNCH(true, CNT_U32);
+    }
+  }
+#undef MGYM_LAUNCH
+}
+
+template <bool ROLLOUT>
+int dispatch(const mgym_env* e, const KernelParams& p, bool vec4, cudaStream_t st) {
+#define MGYM_KIND(K_)                                               \
+  case K_:                                                          \
+    return vec4 ? dispatch_mode<K_, 4, ROLLOUT>(e, p, st) : dispatch_mode<K_, 1, ROLLOUT>(e, p, st)
+  switch (e->kind) {
+    MGYM_KIND(0);
+    MGYM_KIND(1);
+    MGYM_KIND(2);
+    MGYM_KIND(3);
+    MGYM_KIND(4);
+  }
+#undef MGYM_KIND
+  return fail(MGYM_ERR_BAD_ARGUMENT, "bad kind %d", e->kind);
+}
+
+template <int KIND>
+int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* mask, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((p.n + 255) / 256);
+  switch (e->cnt_mode) {
+    case CNT_NONE: reset_kernel<KIND, CNT_NONE><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+    case CNT_U16: reset_kernel<KIND, CNT_U16><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+    default: reset_kernel<KIND, CNT_U32><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+  }
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+int check_bad_action(mgym_env* e, cudaStream_t st) {
+  if (!e->cfg.validate_actions) return MGYM_OK;
+  uint32_t bad = 0;
+  MGYM_CUDA(cudaMemcpyAsync(&bad, e->bad_action, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  if (bad) {
+    MGYM_CUDA(cudaMemsetAsync(e->bad_action, 0, sizeof(uint32_t), st));
+    return fail(MGYM_ERR_INVALID_ACTION, "action outside Discrete(%d) (%s): the reference asserts action_space.contains",
+                kNumActions[e->kind], kNames[e->kind]);
+  }
+  return MGYM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// metadata
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int mgym_abi_version(void) { return MGYM_ABI_VERSION; }
+const char* mgym_last_error(void) { return g_last_error.c_str(); }
+const char* mgym_kind_name(int kind) { return valid_kind(kind) ? kNames[kind] : "?"; }
+int mgym_state_dim(int kind) { return valid_kind(kind) ? kStateDim[kind] : MGYM_ERR_BAD_ARGUMENT; }
+int mgym_obs_dim(int kind) { return valid_kind(kind) ? kObsDim[kind] : MGYM_ERR_BAD_ARGUMENT; }
+int mgym_action_is_continuous(int kind) { return valid_kind(kind) ? kContinuous[kind] : MGYM_ERR_BAD_ARGUMENT; }
+int mgym_num_actions(int kind) { return valid_kind(kind) ? kNumActions[kind] : MGYM_ERR_BAD_ARGUMENT; }
+
+int mgym_space_observation(int kind, float* low, float* high) {
+  if (!valid_kind(kind) || !low || !high) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_space_observation: bad argument");
+  const float inf = std::numeric_limits<float>::infinity();
+  mgym_config cfg{};
+  const EnvConsts k = make_consts(kind, cfg);
+  switch (kind) {
+    case MGYM_CARTPOLE_V1: {  // cartpole.rs:58-64
+      volatile float xt = k.x_threshold, tt = k.theta_threshold;
+      const float hi[4] = {xt * 2.0f, inf, tt * 2.0f, inf};
+      for (int c = 0; c < 4; ++c) high[c] = hi[c], low[c] = -hi[c];
+      break;
+    }
+    case MGYM_MOUNTAIN_CAR_V0:  // mountain_car.rs:42-43
+    case MGYM_MOUNTAIN_CAR_CONTINUOUS_V0:
+      low[0] = k.min_position, low[1] = -k.max_speed, high[0] = k.max_position, high[1] = k.max_speed;
+      break;
+    case MGYM_PENDULUM_V1:
+      low[0] = low[1] = -1.0f, low[2] = -8.0f, high[0] = high[1] = 1.0f, high[2] = 8.0f;
+      break;
+    default:
+      for (int c = 0; c < 4; ++c) low[c] = -1.0f, high[c] = 1.0f;
+      low[4] = -k.max_vel_1, high[4] = k.max_vel_1, low[5] = -k.max_vel_2, high[5] = k.max_vel_2;
+  }
+  return MGYM_OK;
+}
+
+int mgym_space_action(int kind, float* low, float* high) {
+  if (!valid_kind(kind) || !low || !high) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_space_action: bad argument");
+  if (kind == MGYM_MOUNTAIN_CAR_CONTINUOUS_V0) {
+    *low = -1.0f, *high = 1.0f;
+  } else if (kind == MGYM_PENDULUM_V1) {
+    *low = -2.0f, *high = 2.0f;
+  } else {
+    *low = 0.0f, *high = (float)(kNumActions[kind] - 1);  // Discrete(n): {0..n-1}
+  }
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+int mgym_config_default(int kind, mgym_config* cfg) {
+  if (!valid_kind(kind) || !cfg) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_config_default: bad argument");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(mgym_config);
+  cfg->auto_reset = 1;
+  cfg->sutton_barto_reward = 0;  // cartpole.rs:39
+  cfg->is_euler = 1;             // cartpole.rs:40
+  cfg->goal_velocity = 0.0f;     // mountain_car.rs:33
+  cfg->track_stats = 1;
+  cfg->validate_actions = 0;
+  cfg->env_index_base = 0;
+  switch (kind) {
+    case MGYM_MOUNTAIN_CAR_CONTINUOUS_V0: cfg->max_episode_steps = 999; break;
+    case MGYM_PENDULUM_V1: cfg->max_episode_steps = 200; break;
+    case MGYM_ACROBOT_V1: cfg->max_episode_steps = 500; break;
+    default: cfg->max_episode_steps = 0;
+  }
+  return MGYM_OK;
+}
+
+int mgym_destroy(mgym_env* e) {
+  if (!e) return MGYM_OK;
+  DeviceGuard guard(e->device);
+  cudaFree(e->state);
+  cudaFree(e->steps);
+  cudaFree(e->sbt);
+  cudaFree(e->ep_return);
+  cudaFree(e->reset_pool);
+  cudaFree(e->stats);
+  cudaFree(e->bad_action);
+  cudaFree(e->h_actions);
+  cudaFree(e->h_obs);
+  cudaFree(e->h_reward);
+  cudaFree(e->h_flags);
+  delete e;
+  return MGYM_OK;
+}
+
+int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, const mgym_config* cfg_in,
+                mgym_env** out) {
+  if (!out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: out is NULL");
+  *out = nullptr;
+  if (!valid_kind(kind)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: unknown kind %d", kind);
+  if (num_envs == 0) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: num_envs must be > 0");
+  mgym_config cfg;
+  mgym_config_default(kind, &cfg);
+  if (cfg_in) {
+    if (cfg_in->struct_size != sizeof(mgym_config))
+      return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: cfg->struct_size %u != %zu", cfg_in->struct_size,
+                  sizeof(mgym_config));
+    cfg = *cfg_in;
+  }
+  if (cfg.max_episode_steps < 0) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: max_episode_steps < 0");
+
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0)
+    return fail(MGYM_ERR_CUDA, "mgym_create: no CUDA device (%s); there is no CPU fallback",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (device_ordinal < 0 || device_ordinal >= n_dev)
+    return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_create: device %d out of range [0,%d)", device_ordinal, n_dev);
+
+  mgym_env* e = new (std::nothrow) mgym_env();
+  if (!e) return fail(MGYM_ERR_OUT_OF_MEMORY, "mgym_create: host allocation failed");
+  e->kind = kind;
+  e->n = num_envs;
+  e->device = device_ordinal;
+  e->seed = seed;
+  e->cfg = cfg;
+  e->k = make_consts(kind, cfg);
+  e->vec4 = (num_envs % 4 == 0) && (cfg.env_index_base % 4 == 0);
+
+  // counter representation (DESIGN.md "step counters")
+  if (!cfg.auto_reset) {
+    e->cnt_mode = CNT_U32;
+  } else if (kind == MGYM_CARTPOLE_V1) {
+    e->cnt_mode = CNT_U16;  // <= 500 between resets
+  } else if (cfg.max_episode_steps > 0 && cfg.max_episode_steps <= 65535) {
+    e->cnt_mode = CNT_U16;
+  } else if (cfg.max_episode_steps > 65535 || cfg.track_stats) {
+    e->cnt_mode = CNT_U32;
+  } else {
+    e->cnt_mode = CNT_NONE;  // MountainCar-v0 as in the reference: no counter at all
+  }
+
+  DeviceGuard guard(device_ordinal);
+  int rc = [&]() -> int {
+    cudaDeviceProp prop;
+    MGYM_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    e->num_sms = prop.multiProcessorCount;
+    const size_t n = (size_t)num_envs;
+    MGYM_CUDA(cudaMalloc(&e->state, sizeof(float) * kStateDim[kind] * n));
+    MGYM_CUDA(cudaMemset(e->state, 0, sizeof(float) * kStateDim[kind] * n));  // cartpole.rs:85 zero state
+    if (e->cnt_mode != CNT_NONE) {
+      const size_t w = e->cnt_mode == CNT_U16 ? 2 : 4;
+      MGYM_CUDA(cudaMalloc(&e->steps, w * n));
+      MGYM_CUDA(cudaMemset(e->steps, 0, w * n));
+    }
+    if (!cfg.auto_reset && kind == MGYM_CARTPOLE_V1) {
+      MGYM_CUDA(cudaMalloc(&e->sbt, sizeof(uint32_t) * n));
+      fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(e->sbt, 1u, n);  // cartpole.rs:81 Some(0)
+      MGYM_CUDA(cudaGetLastError());
+    }
+    const bool analytic = kind == MGYM_CARTPOLE_V1 || kind == MGYM_MOUNTAIN_CAR_V0 || kind == MGYM_ACROBOT_V1;
+    if (cfg.auto_reset && cfg.track_stats && !analytic) {
+      MGYM_CUDA(cudaMalloc(&e->ep_return, sizeof(float) * n));
+      MGYM_CUDA(cudaMemset(e->ep_return, 0, sizeof(float) * n));
+    }
+    MGYM_CUDA(cudaMalloc(&e->stats, 5 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMemset(e->stats, 0, 5 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMalloc(&e->bad_action, sizeof(uint32_t)));
+    MGYM_CUDA(cudaMemset(e->bad_action, 0, sizeof(uint32_t)));
+    MGYM_CUDA(cudaDeviceSynchronize());
+    return MGYM_OK;
+  }();
+  if (rc != MGYM_OK) {
+    std::string keep = g_last_error;
+    mgym_destroy(e);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = e;
+  return MGYM_OK;
+}
+
+uint64_t mgym_num_envs(const mgym_env* e) { return e ? e->n : 0; }
+int mgym_kind_of(const mgym_env* e) { return e ? e->kind : MGYM_ERR_BAD_ARGUMENT; }
+uint64_t mgym_step_index(const mgym_env* e) { return e ? e->t : 0; }
+float* mgym_state_ptr(mgym_env* e) { return e ? e->state : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// reset
+// ---------------------------------------------------------------------------------------------
+int mgym_reset_masked(mgym_env* e, const uint8_t* mask, float* obs_out, void* stream) {
+  if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_reset: env is NULL");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  KernelParams p = base_params(e);
+  p.obs_out = obs_out;
+  int rc;
+  switch (e->kind) {
+    case 0: rc = launch_reset_kind<0>(e, p, mask, st); break;
+    case 1: rc = launch_reset_kind<1>(e, p, mask, st); break;
+    case 2: rc = launch_reset_kind<2>(e, p, mask, st); break;
+    case 3: rc = launch_reset_kind<3>(e, p, mask, st); break;
+    default: rc = launch_reset_kind<4>(e, p, mask, st); break;
+  }
+  if (rc == MGYM_OK) e->n_resets += 1;
+  return rc;
+}
+
+int mgym_reset(mgym_env* e, float* obs_out, void* stream) { return mgym_reset_masked(e, nullptr, obs_out, stream); }
+
+int mgym_set_reset_pool(mgym_env* e, const float* pool, uint64_t pool_len, void* stream) {
+  if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_set_reset_pool: env is NULL");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(e->reset_pool);
+  e->reset_pool = nullptr;
+  e->pool_len = 0;
+  if (!pool || pool_len == 0) return MGYM_OK;
+  const size_t bytes = sizeof(float) * kStateDim[e->kind] * (size_t)pool_len;
+  MGYM_CUDA(cudaMalloc(&e->reset_pool, bytes));
+  MGYM_CUDA(cudaMemcpyAsync(e->reset_pool, pool, bytes, cudaMemcpyDefault, st));
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  e->pool_len = pool_len;
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state injection / checkpoint
+// ---------------------------------------------------------------------------------------------
+int mgym_set_state(mgym_env* e, const float* state, const uint32_t* steps, const uint32_t* sbt, void* stream) {
+  if (!e || !state) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_set_state: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  MGYM_CUDA(cudaMemcpyAsync(e->state, state, sizeof(float) * kStateDim[e->kind] * n, cudaMemcpyDefault, st));
+  if (e->cnt_mode == CNT_U32) {
+    if (steps) MGYM_CUDA(cudaMemcpyAsync(e->steps, steps, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
+    else MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint32_t) * n, st));
+  } else if (e->cnt_mode == CNT_U16) {
+    if (steps) {
+      convert_kernel<uint32_t, uint16_t><<<blocks, 256, 0, st>>>(steps, (uint16_t*)e->steps, n);
+      MGYM_CUDA(cudaGetLastError());
+    } else {
+      MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint16_t) * n, st));
+    }
+  }
+  if (e->sbt) {
+    if (sbt) MGYM_CUDA(cudaMemcpyAsync(e->sbt, sbt, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
+    else MGYM_CUDA(cudaMemsetAsync(e->sbt, 0, sizeof(uint32_t) * n, st));  // None
+  }
+  if (e->ep_return) MGYM_CUDA(cudaMemsetAsync(e->ep_return, 0, sizeof(float) * n, st));
+  return MGYM_OK;
+}
+
+int mgym_get_state(mgym_env* e, float* state, uint32_t* steps, uint32_t* sbt, void* stream) {
+  if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_get_state: env is NULL");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (state) MGYM_CUDA(cudaMemcpyAsync(state, e->state, sizeof(float) * kStateDim[e->kind] * n, cudaMemcpyDefault, st));
+  if (steps) {
+    if (e->cnt_mode == CNT_U32) {
+      MGYM_CUDA(cudaMemcpyAsync(steps, e->steps, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
+    } else if (e->cnt_mode == CNT_U16) {
+      convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, steps, n);
+      MGYM_CUDA(cudaGetLastError());
+    } else {
+      MGYM_CUDA(cudaMemsetAsync(steps, 0, sizeof(uint32_t) * n, st));
+    }
+  }
+  if (sbt) {
+    if (e->sbt) MGYM_CUDA(cudaMemcpyAsync(sbt, e->sbt, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
+    else MGYM_CUDA(cudaMemsetAsync(sbt, 0, sizeof(uint32_t) * n, st));
+  }
+  return MGYM_OK;
+}
+
+int mgym_get_obs(mgym_env* e, float* obs_out, void* stream) {
+  if (!e || !obs_out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_get_obs: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((e->n + 255) / 256);
+  switch (e->kind) {
+    case 0: obs_kernel<0><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+    case 1: obs_kernel<1><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+    case 2: obs_kernel<2><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+    case 3: obs_kernel<3><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+    default: obs_kernel<4><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+  }
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------------
+int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_out, uint8_t* flags_out,
+              float* final_obs_out, void* stream) {
+  if (!e || !actions) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_step: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  KernelParams p = base_params(e);
+  p.actions = actions;
+  // zero-copy observation: for kinds whose observation is the state, obs_out == state rows is a no-op
+  p.obs_out = (obs_out == e->state) ? nullptr : obs_out;
+  p.reward_out = reward_out;
+  p.flags_out = flags_out;
+  p.final_obs_out = final_obs_out;
+  const bool vec4 = e->vec4 && aligned16(actions) && aligned16(obs_out) && aligned16(reward_out) &&
+                    aligned16(flags_out) && aligned16(final_obs_out);
+  int rc = dispatch<false>(e, p, vec4, st);
+  if (rc != MGYM_OK) return rc;
+  e->t += 1;
+  return check_bad_action(e, st);
+}
+
+int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, float* reward_traj,
+                 uint8_t* flags_traj, unsigned long long* done_count_out, void* stream) {
+  if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_rollout: env is NULL");
+  if (K == 0) return MGYM_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  KernelParams p = base_params(e);
+  p.actions = actions;
+  p.obs_out = obs_traj;
+  p.reward_out = reward_traj;
+  p.flags_out = flags_traj;
+  p.done_count = done_count_out;
+  p.K = K;
+  if (done_count_out) MGYM_CUDA(cudaMemsetAsync(done_count_out, 0, sizeof(unsigned long long), st));
+  const bool vec4 = e->vec4 && aligned16(actions) && aligned16(obs_traj) && aligned16(reward_traj) &&
+                    aligned16(flags_traj);
+  int rc = dispatch<true>(e, p, vec4, st);
+  if (rc != MGYM_OK) return rc;
+  e->t += K;
+  return check_bad_action(e, st);
+}
+
+int mgym_sample_actions(mgym_env* e, void* actions_out, void* stream) {
+  if (!e || !actions_out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_sample_actions: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((e->n + 255) / 256);
+  const uint64_t base = e->cfg.env_index_base;
+  switch (e->kind) {
+    case 0: sample_actions_kernel<0><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
+    case 1: sample_actions_kernel<1><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
+    case 2: sample_actions_kernel<2><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t); break;
+    case 3: sample_actions_kernel<3><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t); break;
+    default: sample_actions_kernel<4><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
+  }
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float* reward_host, uint8_t* flags_host,
+                   void* stream) {
+  if (!e || !actions_host) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_step_host: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  const size_t asz = action_size(e->kind) * n, osz = sizeof(float) * kObsDim[e->kind] * n;
+  if (!e->h_actions) MGYM_CUDA(cudaMalloc(&e->h_actions, asz));
+  if (obs_host && !e->h_obs) MGYM_CUDA(cudaMalloc(&e->h_obs, osz));
+  if (reward_host && !e->h_reward) MGYM_CUDA(cudaMalloc(&e->h_reward, sizeof(float) * n));
+  if (flags_host && !e->h_flags) MGYM_CUDA(cudaMalloc(&e->h_flags, n));
+  MGYM_CUDA(cudaMemcpyAsync(e->h_actions, actions_host, asz, cudaMemcpyHostToDevice, st));
+  int rc = mgym_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, reward_host ? e->h_reward : nullptr,
+                     flags_host ? e->h_flags : nullptr, nullptr, stream);
+  if (rc != MGYM_OK) return rc;
+  if (obs_host) MGYM_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, osz, cudaMemcpyDeviceToHost, st));
+  if (reward_host) MGYM_CUDA(cudaMemcpyAsync(reward_host, e->h_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if (flags_host) MGYM_CUDA(cudaMemcpyAsync(flags_host, e->h_flags, n, cudaMemcpyDeviceToHost, st));
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------
+int mgym_stats_get(mgym_env* e, mgym_stats_t* out, void* stream) {
+  if (!e || !out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_stats_get: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long raw[5];
+  MGYM_CUDA(cudaMemcpyAsync(raw, e->stats, sizeof(raw), cudaMemcpyDeviceToHost, st));
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  out->episodes = raw[0];
+  out->terminated = raw[1];
+  out->truncated = raw[2];
+  out->length_sum = raw[3];
+  memcpy(&out->return_sum, &raw[4], sizeof(double));
+  return MGYM_OK;
+}
+
+int mgym_stats_reset(mgym_env* e, void* stream) {
+  if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_stats_reset: env is NULL");
+  DeviceGuard guard(e->device);
+  MGYM_CUDA(cudaMemsetAsync(e->stats, 0, 5 * sizeof(unsigned long long), (cudaStream_t)stream));
+  return MGYM_OK;
+}
+
+int mgym_stats_export(mgym_env* e, double* device_vec5_out, void* stream) {
+  if (!e || !device_vec5_out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_stats_export: NULL argument");
+  DeviceGuard guard(e->device);
+  stats_export_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->stats, device_vec5_out);
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+int mgym_stats_allreduce(mgym_env* e, void* nccl_comm, double* device_vec5_out, void* stream) {
+  if (!e || !nccl_comm || !device_vec5_out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_stats_allreduce: NULL argument");
+  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+  using allreduce_fn = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = [] {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!sym) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) sym = dlsym(h, "ncclAllReduce");
+    }
+    return reinterpret_cast<allreduce_fn>(sym);
+  }();
+  if (!fn) return fail(MGYM_ERR_NCCL, "mgym_stats_allreduce: ncclAllReduce not found in this process or libnccl.so.2");
+  int rc = mgym_stats_export(e, device_vec5_out, stream);
+  if (rc != MGYM_OK) return rc;
+  DeviceGuard guard(e->device);
+  constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+  const int nrc = fn(device_vec5_out, device_vec5_out, 5, kNcclFloat64, kNcclSum, nccl_comm, (cudaStream_t)stream);
+  if (nrc != 0) return fail(MGYM_ERR_NCCL, "ncclAllReduce returned %d", nrc);
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test probes (not part of include/mgym.h): device sin/cos and Philox for the parity tests
+// ---------------------------------------------------------------------------------------------
+int mgym_probe_trig(const float* x, float* s, float* c, float* s_only, float* c_only, uint64_t n, void* stream) {
+  trig_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, s, c, s_only, c_only, n);
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+int mgym_probe_philox(const uint32_t* ctr_key, uint32_t* out, uint64_t n, void* stream) {
+  philox_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctr_key, out, n);
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+}  // extern "C"

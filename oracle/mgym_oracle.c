@@ -583,14 +583,16 @@ void oracle_reset_state(int kind, uint64_t seed, uint64_t g, uint64_t t, uint32_
 }
 
 void oracle_sample_action(int kind, uint64_t seed, uint64_t g, uint64_t t, uint8_t *a_u8, float *a_f32) {
-  uint32_t w[4];
-  philox_env(seed, g, t, 2u, w);
+  /* one Philox block serves 4 consecutive envs: block index g >> 2, word g & 3 */
+  uint32_t w4[4];
+  philox_env(seed, g >> 2, t, 2u, w4);
+  const uint32_t w = w4[g & 3];
   switch (kind) {
-    case ORACLE_CARTPOLE_V1: *a_u8 = (uint8_t)(((uint64_t)w[0] * 2u) >> 32); break;
+    case ORACLE_CARTPOLE_V1: *a_u8 = (uint8_t)(((uint64_t)w * 2u) >> 32); break;
     case ORACLE_MOUNTAIN_CAR_V0:
-    case ORACLE_ACROBOT_V1: *a_u8 = (uint8_t)(((uint64_t)w[0] * 3u) >> 32); break;
-    case ORACLE_MOUNTAIN_CAR_CONTINUOUS_V0: *a_f32 = uniform_f64_to_f32(w[0], -1.0, 1.0); break;
-    default: *a_f32 = uniform_f64_to_f32(w[0], -2.0, 2.0);
+    case ORACLE_ACROBOT_V1: *a_u8 = (uint8_t)(((uint64_t)w * 3u) >> 32); break;
+    case ORACLE_MOUNTAIN_CAR_CONTINUOUS_V0: *a_f32 = uniform_f64_to_f32(w, -1.0, 1.0); break;
+    default: *a_f32 = uniform_f64_to_f32(w, -2.0, 2.0);
   }
 }
 

@@ -1,0 +1,487 @@
+"""Parity of the CUDA path (through the C ABI, via GpuVecEnv) against the CPU oracle.
+
+Bar (BASELINE.json north_star): terminated/truncated flags and step counts bit-exact; states and
+rewards within 1e-6 relative for CartPole/MountainCar and 1e-5 for the others.  Because the
+device code restates glibc's sinf/cosf exactly and never fuses a multiply-add, the tests below
+hold every value to BIT equality, which implies both tolerances."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (CONTINUOUS, KIND_NAMES, NUM_ACTIONS, OBS_DIM, STATE_DIM, assert_bit_equal, random_actions,
+                     random_states)
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = {0: 1e-6, 1: 1e-6, 2: 1e-5, 3: 1e-5, 4: 1e-5}  # north_star tolerances (documented; we get 0)
+
+
+@pytest.fixture(scope="module")
+def gym():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import modurl_gym_b200 as m
+
+    m.load_library()  # fails loudly if libmgym.so is missing
+    return m
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks: sin/cos and Philox on the device
+# ---------------------------------------------------------------------------------------------
+def test_device_trig_bit_exact(gym, oracle):
+    import ctypes as C
+
+    lib = gym.load_library()
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([
+        rng.uniform(-0.3, 0.3, 200000), rng.uniform(-4, 4, 200000), rng.uniform(-130, 130, 200000),
+        rng.standard_normal(100000) * 1e4, rng.standard_normal(50000) * 1e30,
+        np.array([0.0, -0.0, 2.0 ** -12, -(2.0 ** -12), np.nextafter(np.float32(2.0 ** -12), 0), 0.7853982, 0.78539819,
+                  -0.7853982, 120.0, 119.99999, -120.0, 1e-40, -1e-40, 3.4e38, -3.4e38, np.inf, -np.inf, np.nan]),
+        np.arange(-200, 200) * (np.pi / 4),
+    ]).astype(np.float32)
+    # the bit patterns around the CartPole and MountainCar working ranges, densely
+    xs = np.concatenate([xs, np.arange(0x3e567750 - 50000, 0x3e567750 + 50000, dtype=np.uint32).view(np.float32)])
+    x = dev(xs)
+    outs = [torch.empty_like(x) for _ in range(4)]
+    rc = lib.mgym_probe_trig(C.c_void_p(x.data_ptr()), *[C.c_void_p(o.data_ptr()) for o in outs], x.numel(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    s, c, s_only, c_only = [host(o) for o in outs]
+    ws = np.array([oracle.sinf(v) for v in xs], dtype=np.float32)
+    wc = np.array([oracle.cosf(v) for v in xs], dtype=np.float32)
+    finite = np.isfinite(xs)
+    assert_bit_equal(s[finite], ws[finite], "sincos.sin")
+    assert_bit_equal(c[finite], wc[finite], "sincos.cos")
+    assert_bit_equal(s_only[finite], ws[finite], "sin_ref")
+    assert_bit_equal(c_only[finite], wc[finite], "cos_ref")
+    assert np.isnan(s[~finite]).all() and np.isnan(c[~finite]).all()
+
+
+def test_device_philox_known_answers(gym, oracle):
+    import ctypes as C
+
+    lib = gym.load_library()
+    rng = np.random.default_rng(3)
+    ck = rng.integers(0, 2 ** 32, size=(4096, 6), dtype=np.uint64).astype(np.uint32)
+    ck[0] = 0
+    ck[1] = 0xFFFFFFFF
+    ck[2] = [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0]
+    d = dev(ck)
+    out = torch.empty((4096, 4), dtype=torch.int32, device="cuda")
+    assert lib.mgym_probe_philox(C.c_void_p(d.data_ptr()), C.c_void_p(out.data_ptr()), 4096, None) == 0
+    got = host(out).view(np.uint32)
+    # Random123 known-answer vectors
+    assert got[0].tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert got[1].tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert got[2].tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    want = np.stack([oracle.philox(r[:4], r[4:]) for r in ck[:512]])
+    assert_bit_equal(got[:512], want, "philox")
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own known-answer test, replayed on the GPU (src/testing.rs:34-146)
+# ---------------------------------------------------------------------------------------------
+def load_golden(name):
+    with open(os.path.join(GOLDEN, f"{name}_gymnasium.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name,kind", [("cartpole", 0), ("mountain_car", 1)])
+def test_gym_against_python_scalar(gym, name, kind):
+    """One env, 100 teacher-forced steps, exactly the loop of testing.rs:65-134."""
+    doc = load_golden(name)
+    env = gym.GpuVecEnv(kind, 1, auto_reset=False)
+    sd = STATE_DIM[kind]
+    zeros = torch.zeros((sd, 1))
+    env.reset()                      # reset_deterministic(): reset() then zero state (cartpole.rs:437-442)
+    env.set_state(zeros)
+    for i, action in enumerate(doc["actions"]):
+        if i == 0 or doc["done"][i - 1]:
+            env.reset()
+            env.set_state(zeros)
+        else:
+            # set_state only overwrites the state tensor (cartpole.rs:444-446): keep the counters
+            _, steps, sbt = env.get_state()
+            env.set_state(torch.tensor(doc["observation"][i - 1], dtype=torch.float32).reshape(sd, 1), steps, sbt)
+        info = env.step(torch.tensor([action], dtype=torch.uint8, device="cuda"))
+        obs = host(info.state)[:, 0]
+        assert abs(float(info.reward[0]) - doc["reward"][i]) <= 1e-4                 # testing.rs:99
+        assert bool(info.done[0]) == doc["done"][i], f"done mismatch at step {i + 1}"          # :106
+        assert bool(info.truncated[0]) == doc["truncated"][i], f"truncated mismatch at {i + 1}"  # :114
+        assert np.max(np.abs(obs - np.asarray(doc["observation"][i]))) < 2e-7        # :124-133 (1e-4 there)
+    env.close()
+
+
+@pytest.mark.parametrize("name,kind", [("cartpole", 0), ("mountain_car", 1)])
+def test_gym_against_python_batched(gym, oracle, name, kind):
+    """The same 100 teacher-forced transitions as ONE batched step: env i replays fixture step i."""
+    doc = load_golden(name)
+    n, sd = 100, STATE_DIM[kind]
+    start = np.zeros((sd, n), dtype=np.float32)
+    for i in range(1, n):
+        if not doc["done"][i - 1]:
+            start[:, i] = doc["observation"][i - 1]
+    env = gym.GpuVecEnv(kind, n, auto_reset=False)
+    env.reset()
+    env.set_state(dev(start))
+    info = env.step(dev(np.asarray(doc["actions"], dtype=np.uint8)))
+    obs = host(info.state)
+    assert np.max(np.abs(obs.T - np.asarray(doc["observation"]))) < 2e-7
+    assert host(info.done).tolist() == doc["done"]
+    assert host(info.truncated).tolist() == doc["truncated"]
+    assert host(info.reward).tolist() == doc["reward"]
+    # and bit-exact against the oracle on the same inputs
+    ref = oracle.VecState(kind, n, auto_reset=0)
+    ref.reset()
+    ref.state[:] = start
+    o, r, f = ref.step(np.asarray(doc["actions"], dtype=np.uint8))
+    assert_bit_equal(obs, o, "obs")
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 1: one CartPole env, 10^4 random-action steps, injected reset states
+# ---------------------------------------------------------------------------------------------
+def test_cartpole_single_env_trace_1e4(gym, oracle):
+    T = 10_000
+    rng = np.random.default_rng(123)
+    pool = rng.uniform(-0.05, 0.05, size=(4, T + 1)).astype(np.float32)
+    actions = rng.integers(0, 2, size=T, dtype=np.uint8)
+    env = gym.GpuVecEnv(0, 1, auto_reset=True, seed=1)
+    env.set_reset_pool(dev(pool))
+    env.set_state(dev(pool[:, :1]))
+    ref = oracle.VecState(0, 1, auto_reset=1, seed=1)
+    ref.set_reset_pool(pool)
+    ref.state[:] = pool[:, :1]
+    ref.sbt[:] = 0
+    # per-call steps on the GPU ...
+    a_dev = dev(actions.reshape(T, 1))
+    got_obs = np.zeros((T, 4), np.float32)
+    got_rew = np.zeros(T, np.float32)
+    got_flg = np.zeros(T, np.uint8)
+    got_steps = np.zeros(T, np.uint32)
+    obs_all = torch.empty((T, 4, 1), device="cuda")
+    rew_all = torch.empty((T, 1), device="cuda")
+    flg_all = torch.empty((T, 1), dtype=torch.uint8, device="cuda")
+    stp_all = torch.empty((T, 1), dtype=torch.int32, device="cuda")
+    import ctypes as C
+    lib = gym.load_library()
+    for t in range(T):
+        env.step_raw(a_dev[t], obs_all[t], rew_all[t], flg_all[t])
+        lib.mgym_get_state(env._h, None, C.c_void_p(stp_all[t].data_ptr()), None, None)
+    got_obs[:] = host(obs_all)[:, :, 0]
+    got_rew[:] = host(rew_all)[:, 0]
+    got_flg[:] = host(flg_all)[:, 0]
+    got_steps[:] = host(stp_all)[:, 0].view(np.uint32)
+    # ... against the oracle
+    n_done = 0
+    for t in range(T):
+        o, r, f = ref.step(actions[t:t + 1])
+        assert got_flg[t] == f[0], f"flags differ at step {t}"
+        assert got_steps[t] == ref.steps[0], f"step counter differs at step {t}"
+        assert_bit_equal(got_obs[t], o[:, 0], f"obs at step {t}")
+        assert got_rew[t] == r[0]
+        n_done += int(f[0] != 0)
+    assert n_done > 300  # random policy: ~22 steps per episode
+    rel = np.max(np.abs(got_obs - got_obs) / np.maximum(np.abs(got_obs), 1e-30))
+    assert rel <= REL_TOL[0]
+    s = env.stats()
+    assert s.episodes == n_done == ref.stats.episodes and s.length_sum == ref.stats.length_sum
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched auto-reset parity, all five kinds, vector (N % 4 == 0) and scalar-lane (ragged N) paths
+# ---------------------------------------------------------------------------------------------
+def run_auto_parity(gym, oracle, kind, n, T, seed, use_pool=False, want_final=False, **cfg):
+    rng = np.random.default_rng(1000 + kind)
+    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=seed, **cfg)
+    ocfg = {k: v for k, v in cfg.items() if k in ("max_episode_steps", "sutton_barto_reward", "is_euler",
+                                                    "goal_velocity", "env_index_base")}
+    ocfg = {k: (int(v) if k != "goal_velocity" else v) for k, v in ocfg.items()}
+    ref = oracle.VecState(kind, n, auto_reset=1, seed=seed, **ocfg)
+    if use_pool:
+        pool = random_states(rng, kind, 257)
+        env.set_reset_pool(dev(pool))
+        ref.set_reset_pool(pool)
+    o0 = host(env.reset())
+    assert_bit_equal(o0, ref.reset(), "reset obs")
+    if kind != 0:  # start some envs from broad states too
+        st = random_states(rng, kind, n)
+        env.set_state(dev(st))
+        ref.state[:] = st
+        ref.steps[:] = 0
+    for t in range(T):
+        a = random_actions(rng, kind, n)
+        if want_final:
+            info, fin = env.step(dev(a), want_final_obs=True)
+            o, r, f, fo = ref.step(a, want_final_obs=True)
+            assert_bit_equal(host(fin), fo, f"final obs t={t}")
+        else:
+            info = env.step(dev(a))
+            o, r, f = ref.step(a)
+        flags = host(info.done).astype(np.uint8) | (host(info.truncated).astype(np.uint8) << 1)
+        assert_bit_equal(flags, f, f"{KIND_NAMES[kind]} flags t={t}")
+        assert_bit_equal(host(info.state), o, f"{KIND_NAMES[kind]} obs t={t}")
+        assert_bit_equal(host(info.reward), r, f"{KIND_NAMES[kind]} reward t={t}")
+    state, steps, _ = env.get_state()
+    assert_bit_equal(host(state), ref.state, "final state")
+    assert_bit_equal(host(steps).view(np.uint32), ref.steps, "step counters")
+    s = env.stats()
+    assert (s.episodes, s.terminated, s.truncated, s.length_sum) == (
+        ref.stats.episodes, ref.stats.terminated, ref.stats.truncated, ref.stats.length_sum)
+    assert s.return_sum == pytest.approx(ref.stats.return_sum, rel=1e-9, abs=1e-6)
+    env.close()
+    return s
+
+
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("n", [2048, 1027])
+def test_auto_reset_parity(gym, oracle, kind, n):
+    T = {0: 600, 1: 300, 2: 300, 3: 250, 4: 200}[kind]
+    s = run_auto_parity(gym, oracle, kind, n, T, seed=0x5EED)
+    if kind in (0, 3, 4):
+        assert s.episodes > 0
+
+
+def test_cartpole_truncation_at_500(gym, oracle):
+    """cartpole.rs:296-306: an env that survives 500 steps truncates with done=false, reward 1."""
+    n = 64
+    env = gym.GpuVecEnv(0, n, auto_reset=True, seed=5)
+    ref = oracle.VecState(0, n, auto_reset=1, seed=5)
+    env.reset(), ref.reset()
+    z = np.zeros((4, n), np.float32)
+    steps = np.full(n, 497, np.uint32)
+    env.set_state(dev(z), dev(steps.view(np.int32)))
+    ref.state[:] = z
+    ref.steps[:] = steps
+    seen_trunc = False
+    for t in range(6):
+        a = np.full(n, t % 2, np.uint8)
+        info = env.step(dev(a))
+        o, r, f = ref.step(a)
+        flags = host(info.done).astype(np.uint8) | (host(info.truncated).astype(np.uint8) << 1)
+        assert_bit_equal(flags, f, f"flags t={t}")
+        assert_bit_equal(host(info.state), o, f"obs t={t}")
+        if t == 2:
+            assert (flags == 2).all() and (host(info.reward) == 1.0).all()
+            seen_trunc = True
+    assert seen_trunc
+
+
+@pytest.mark.parametrize("kind,cfg", [
+    (0, dict(sutton_barto_reward=True)),
+    (0, dict(is_euler=False)),
+    (1, dict(goal_velocity=0.02)),
+    (1, dict(max_episode_steps=200)),
+    (2, dict(max_episode_steps=50)),
+    (0, dict(env_index_base=4096)),
+    (4, dict(env_index_base=6)),       # unaligned slice base: scalar-lane path
+])
+def test_auto_reset_parity_options(gym, oracle, kind, cfg):
+    run_auto_parity(gym, oracle, kind, 1024, 260, seed=99, **cfg)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 3])
+def test_auto_reset_injected_pool_and_final_obs(gym, oracle, kind):
+    run_auto_parity(gym, oracle, kind, 1024, 200, seed=3, use_pool=True, want_final=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# manual mode: the reference's own semantics, including stepping past termination
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("sb", [False, True])
+def test_manual_mode_parity(gym, oracle, kind, sb):
+    if sb and kind != 0:
+        pytest.skip("sutton_barto_reward is a CartPole option")
+    n, T = 1024, 120
+    rng = np.random.default_rng(50 + kind)
+    env = gym.GpuVecEnv(kind, n, auto_reset=False, seed=11, sutton_barto_reward=sb)
+    ref = oracle.VecState(kind, n, auto_reset=0, seed=11, sutton_barto_reward=int(sb))
+    # before any reset the reference env holds a zero state and steps_beyond_terminated = Some(0)
+    _, steps, sbt = env.get_state()
+    assert_bit_equal(host(sbt).view(np.uint32), ref.sbt, "initial sbt")
+    for t in range(T):
+        if t == 40:   # caller-side reset of the envs that are done, cartpole.rs:468-470
+            mask = (last_flags != 0).astype(np.uint8)
+            assert_bit_equal(host(env.reset(mask=dev(mask))), ref.reset(mask=mask), "masked reset obs")
+        if t == 80:
+            assert_bit_equal(host(env.reset()), ref.reset(), "reset obs")
+        a = random_actions(rng, kind, n)
+        info = env.step(dev(a))
+        o, r, f = ref.step(a)
+        last_flags = host(info.done).astype(np.uint8) | (host(info.truncated).astype(np.uint8) << 1)
+        assert_bit_equal(last_flags, f, f"flags t={t}")
+        assert_bit_equal(host(info.state), o, f"obs t={t}")
+        assert_bit_equal(host(info.reward), r, f"reward t={t}")
+    state, steps, sbt = env.get_state()
+    assert_bit_equal(host(steps).view(np.uint32), ref.steps, "steps_since_reset")
+    if kind == 0:
+        assert_bit_equal(host(sbt).view(np.uint32), ref.sbt, "steps_beyond_terminated")
+        assert (ref.sbt > 1).any()  # the post-termination branch (cartpole.rs:330-347) was exercised
+    env.close()
+
+
+def test_mountain_car_wall_and_goal(gym, oracle):
+    """mountain_car.rs:311-313 (left wall) and :318 (goal), which no reference fixture reaches."""
+    st = np.array([[-1.2, -1.2, -1.19, 0.49, 0.5, 0.499],
+                   [-0.01, 0.0, -0.07, 0.07, 0.0, 0.069]], dtype=np.float32)
+    a = np.array([0, 2, 0, 2, 2, 2], dtype=np.uint8)
+    env = gym.GpuVecEnv(1, 6, auto_reset=False)
+    env.set_state(dev(st))
+    info = env.step(dev(a))
+    ref = oracle.VecState(1, 6, auto_reset=0)
+    ref.state[:] = st
+    o, r, f = ref.step(a)
+    obs = host(info.state)
+    assert_bit_equal(obs, o, "obs")
+    assert obs[0, 0] == np.float32(-1.2) and obs[1, 0] == 0.0     # stopped by the wall
+    assert host(info.done).tolist() == [bool(x & 1) for x in f]
+    assert host(info.done)[3] and host(info.done)[4]               # reached the goal
+    assert not host(info.truncated).any() and (host(info.reward) == -1.0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# rollout mode
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("n,policy", [(1024, False), (1024, True), (515, True), (515, False)])
+def test_rollout_parity(gym, oracle, kind, n, policy):
+    K = {0: 300, 1: 200, 2: 200, 3: 210, 4: 120}[kind]
+    rng = np.random.default_rng(70 + kind)
+    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=0xABCDEF)
+    ref = oracle.VecState(kind, n, auto_reset=1, seed=0xABCDEF)
+    env.reset(), ref.reset()
+    for chunk in range(2):  # two consecutive rollouts: the step index carries over
+        a = None if policy else random_actions(rng, kind, (K, n))
+        out = env.rollout(K, None if policy else dev(a))
+        o, r, f, dc = ref.rollout(K, a)
+        assert_bit_equal(host(out.flags), f, f"flags chunk {chunk}")
+        assert_bit_equal(host(out.obs), o, f"obs chunk {chunk}")
+        assert_bit_equal(host(out.reward), r, f"reward chunk {chunk}")
+        assert int(out.done_count.item()) == dc == int((f != 0).sum())
+    state, steps, _ = env.get_state()
+    assert_bit_equal(host(state), ref.state, "state after rollout")
+    assert_bit_equal(host(steps).view(np.uint32), ref.steps, "steps after rollout")
+    s = env.stats()
+    assert (s.episodes, s.length_sum) == (ref.stats.episodes, ref.stats.length_sum)
+    assert s.return_sum == pytest.approx(ref.stats.return_sum, rel=1e-9, abs=1e-6)
+    env.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_rollout_equals_repeated_steps(gym, kind):
+    """Mode equivalence: K fused steps == K per-call steps with the sampled actions (bitwise)."""
+    n, K = 4096, 64
+    a_env = gym.GpuVecEnv(kind, n, seed=21)
+    b_env = gym.GpuVecEnv(kind, n, seed=21)
+    a_env.reset(), b_env.reset()
+    out = a_env.rollout(K)
+    for k in range(K):
+        acts = b_env.sample_actions()
+        info = b_env.step(acts)
+        assert torch.equal(info.state.view(torch.int32), out.obs[k].view(torch.int32))
+        assert torch.equal(info.reward, out.reward[k])
+        flags = info.done.to(torch.uint8) | (info.truncated.to(torch.uint8) << 1)
+        assert torch.equal(flags, out.flags[k])
+    assert a_env.stats() == b_env.stats()
+
+
+def test_sample_actions_matches_oracle(gym, oracle):
+    for kind in range(5):
+        env = gym.GpuVecEnv(kind, 64, seed=77, env_index_base=8)
+        got = host(env.sample_actions())
+        want = np.array([oracle.sample_action(kind, 77, 8 + i, 0) for i in range(64)], dtype=got.dtype)
+        assert_bit_equal(got, want, KIND_NAMES[kind])
+        if not CONTINUOUS[kind]:
+            assert got.max() < NUM_ACTIONS[kind]
+
+
+# ---------------------------------------------------------------------------------------------
+# API behaviour
+# ---------------------------------------------------------------------------------------------
+def test_invalid_action_is_reported(gym):
+    """cartpole.rs:392-403 / mountain_car.rs:374-385: the reference panics; the ABI returns an error."""
+    for kind, bad in [(0, 2), (1, 3)]:
+        env = gym.GpuVecEnv(kind, 8, validate_actions=True)
+        env.reset()
+        a = torch.zeros(8, dtype=torch.uint8, device="cuda")
+        env.step(a)
+        a[5] = bad
+        with pytest.raises(gym.InvalidActionError):
+            env.step(a)
+        env.step(torch.zeros(8, dtype=torch.uint8, device="cuda"))  # the handle stays usable
+    env = gym.GpuVecEnv(0, 8)
+    with pytest.raises(TypeError):
+        env.step(torch.zeros(8, dtype=torch.int64, device="cuda"))   # wrong dtype (u32 scalar in the reference)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((8, 1), dtype=torch.uint8, device="cuda"))  # wrong rank, cartpole.rs:392-403
+
+
+def test_reset_distribution_and_determinism(gym):
+    """cartpole.rs:240: U[-0.05, 0.05); mountain_car.rs:281-283: U[-0.6,-0.4), v = 0; same seed => same stream
+    (cartpole.rs:474-517), independent of how envs are split over handles."""
+    n = 1 << 16
+    e1 = gym.GpuVecEnv(0, n, seed=42)
+    o1 = host(e1.reset()).copy()
+    assert o1.min() >= -0.05 and o1.max() <= 0.05
+    assert abs(o1.mean()) < 1e-3 and abs(o1.std() - 0.1 / np.sqrt(12)) < 1e-3
+    e2 = gym.GpuVecEnv(0, n, seed=42)
+    assert_bit_equal(host(e2.reset()), o1, "same seed")
+    halves = [gym.GpuVecEnv(0, n // 2, seed=42, env_index_base=b) for b in (0, n // 2)]
+    assert_bit_equal(np.concatenate([host(h.reset()) for h in halves], axis=1), o1, "sharded reset")
+    e3 = gym.GpuVecEnv(0, n, seed=43)
+    assert (host(e3.reset()) != o1).mean() > 0.99
+    m = gym.GpuVecEnv(1, n, seed=42)
+    om = host(m.reset())
+    assert om[0].min() >= -0.6 and om[0].max() <= -0.4 and (om[1] == 0).all()
+
+
+def test_sharded_handles_equal_one_handle(gym):
+    """results are independent of the number of GPUs the env range is split over."""
+    n, K = 8192, 50
+    whole = gym.GpuVecEnv(0, n, seed=9)
+    whole.reset()
+    ow = whole.rollout(K)
+    parts = [gym.GpuVecEnv(0, n // 4, seed=9, env_index_base=b * (n // 4)) for b in range(4)]
+    outs = []
+    for p in parts:
+        p.reset()
+        outs.append(p.rollout(K))
+    assert torch.equal(torch.cat([o.obs for o in outs], dim=2).view(torch.int32), ow.obs.view(torch.int32))
+    assert torch.equal(torch.cat([o.flags for o in outs], dim=1), ow.flags)
+    tot = [sum(x) for x in zip(*[p.stats() for p in parts])]
+    assert tuple(tot[:4]) == tuple(whole.stats()[:4])
+
+
+def test_step_host_round_trip(gym, oracle):
+    n = 4096
+    env = gym.GpuVecEnv(0, n, seed=2)
+    ref = oracle.VecState(0, n, auto_reset=1, seed=2)
+    env.reset(), ref.reset()
+    rng = np.random.default_rng(0)
+    obs = torch.empty((4, n)).pin_memory()
+    rew = torch.empty(n).pin_memory()
+    flg = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(30):
+        a = random_actions(rng, 0, n)
+        env.step_host(torch.from_numpy(a).pin_memory(), obs, rew, flg)
+        o, r, f = ref.step(a)
+        assert_bit_equal(obs.numpy(), o, "obs")
+        assert_bit_equal(flg.numpy(), f, "flags")
+        assert_bit_equal(rew.numpy(), r, "reward")
