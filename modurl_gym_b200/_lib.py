@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmgym.so")
+# MGYM_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("MGYM_LIB") or os.path.join(HERE, "libmgym.so")
 
 OK = 0
 ERR_BAD_ARGUMENT, ERR_CUDA, ERR_NCCL, ERR_INVALID_ACTION, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
@@ -84,6 +85,8 @@ SYMBOLS = {
 PROBES = {
     "mgym_probe_trig": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "mgym_probe_philox": (_i, [_vp, _vp, _u64, _vp]),
+    "mgym_probe_fast_exhaustive": (_i, [_i, _u64, _u64, _vp]),
+    "mgym_probe_fast_div_random": (_i, [_u64, _u64, _vp]),
 }
 
 _lib = None

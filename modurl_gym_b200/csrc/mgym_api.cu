@@ -100,6 +100,7 @@ EnvConsts make_consts(int kind, const mgym_config& cfg) {
   k.gravity = 9.8f;
   k.masspole = masspole;
   k.total_mass = masspole + masscart;
+  k.rcp_total_mass = (float)(1.0 / (double)k.total_mass);  // RN(1/total_mass), see fdiv_const_fast
   k.length = length;
   k.polemass_length = masspole * length;
   k.force_mag = 10.0f;
@@ -691,6 +692,37 @@ int mgym_stats_allreduce(mgym_env* e, void* nccl_comm, double* device_vec5_out, 
 int mgym_probe_trig(const float* x, float* s, float* c, float* s_only, float* c_only, uint64_t n, void* stream) {
   trig_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, s, c, s_only, c_only, n);
   MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+// mode 0/1/2 of fast_exhaustive_kernel over bit patterns [first, first+n); out = {checked, bad, first_bad}
+int mgym_probe_fast_exhaustive(int mode, uint64_t first, uint64_t n, uint64_t* out3) {
+  unsigned long long* d = nullptr;
+  MGYM_CUDA(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  MGYM_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  MGYM_CUDA(cudaMemset(d + 2, 0xff, sizeof(unsigned long long)));
+  mgym_config cfg{};
+  const EnvConsts k = make_consts(0, cfg);
+  fast_exhaustive_kernel<<<148 * 8, 256>>>(mode, first, n, k.total_mass, k.rcp_total_mass, d, d + 1,
+                                           reinterpret_cast<uint32_t*>(d + 2));
+  MGYM_CUDA(cudaGetLastError());
+  unsigned long long h[3];
+  MGYM_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  out3[0] = h[0], out3[1] = h[1], out3[2] = (uint32_t)h[2];
+  return MGYM_OK;
+}
+
+int mgym_probe_fast_div_random(uint64_t seed, uint64_t n, uint64_t* out2) {
+  unsigned long long* d = nullptr;
+  MGYM_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  MGYM_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  fast_div_random_kernel<<<148 * 8, 256>>>(seed, n, d, d + 1);
+  MGYM_CUDA(cudaGetLastError());
+  unsigned long long h[2];
+  MGYM_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  out2[0] = h[0], out2[1] = h[1];
   return MGYM_OK;
 }
 

@@ -12,6 +12,10 @@
 
 #include "mgym_device.cuh"
 
+#ifndef MGYM_MIN_BLOCKS
+#define MGYM_MIN_BLOCKS 1
+#endif
+
 namespace mgym {
 
 enum CounterMode : int { CNT_NONE = 0, CNT_U16 = 1, CNT_U32 = 2 };
@@ -127,47 +131,91 @@ __device__ __forceinline__ void stats_flush(const StatAcc& a, const KernelParams
   }
 }
 
-// ---- one env: step, then (AUTO) same-step reset --------------------------------------------
-// Returns flags.  st / steps / sbt / ret are updated in place; obs holds the observation the
-// caller sees (post-reset when the episode ended), fin the pre-reset observation.
-template <int KIND, bool AUTO, bool WANT_FINAL>
-__device__ __forceinline__ uint32_t env_transition(const KernelParams& p, bool count, uint64_t local_index, uint64_t t,
-                                                   typename Env<KIND>::act_t action, float (&st)[Env<KIND>::SD],
-                                                   uint32_t& steps, uint32_t& sbt, float& ret, bool track_ret,
-                                                   float& reward, float (&obs)[Env<KIND>::OD],
-                                                   float (&fin)[Env<KIND>::OD], StatAcc& acc) {
+// ---- V consecutive envs: step, then (AUTO) same-step reset --------------------------------
+// Phase 1 runs the branch-free dynamics of all V envs back to back (independent chains the
+// scheduler can interleave); an env whose fast-path precondition fails is redone with the
+// reference form.  Phase 2 serves the finished envs one per lane per pass: a lane with one
+// finished env draws ONE Philox block, whichever of its V slots that env sits in, so a warp
+// runs the reset code about once per step instead of once per slot.
+template <int KIND, int V>
+struct Group {
   using E = Env<KIND>;
-  if constexpr (AUTO) sbt = SBT_NONE;  // auto-reset presumes reset() precedes every episode
-  const uint32_t flags = E::step(st, action, steps, sbt, p.k, reward);
-  if (track_ret) ret = fadd(ret, reward);
-  E::obs(st, obs);
-  if constexpr (WANT_FINAL) {
+  float st[V][E::SD];
+  uint32_t steps[V], sbt[V];
+  float ret[V];
+  // per-step outputs
+  float obs[V][E::OD], fin[V][E::OD], reward[V];
+  uint32_t flags[V];
+};
+
+template <int KIND, int V, bool AUTO, bool WANT_FINAL>
+__device__ __forceinline__ void step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
+                                           const typename Env<KIND>::act_t (&action)[V], bool track_ret,
+                                           Group<KIND, V>& g, StatAcc& acc) {
+  using E = Env<KIND>;
+  float aux[V];
+  bool ok[V];
+  bool all_ok = true;
 #pragma unroll
-    for (int c = 0; c < E::OD; ++c) fin[c] = obs[c];
+  for (int v = 0; v < V; ++v) {
+    aux[v] = 0.0f;
+    ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
+    all_ok = all_ok && ok[v];
   }
-  if constexpr (AUTO) {
-    if (flags) {
-      if (count) {
-        acc.episodes += 1;
-        acc.terminated += (flags & FLAG_TERMINATED) ? 1u : 0u;
-        acc.truncated += (flags & FLAG_TRUNCATED) ? 1u : 0u;
-        acc.length_sum += steps;
-        acc.return_sum += (double)(E::ANALYTIC_RETURN ? E::episode_return(p.k, steps, flags) : ret);
-      }
-      const uint64_t g = p.env_base + local_index;
-      if (p.reset_pool) {
-        const uint64_t j = (g + t) % p.pool_len;
+  if (!all_ok) {
 #pragma unroll
-        for (int c = 0; c < E::SD; ++c) st[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
-      } else {
-        E::reset(philox_env(p.seed, g, t, TAG_AUTO_RESET), st);
+    for (int v = 0; v < V; ++v)
+      if (!ok[v]) E::dynamics(g.st[v], action[v], p.k, aux[v]);
+  }
+  uint32_t pending = 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if constexpr (AUTO) g.sbt[v] = SBT_NONE;  // auto-reset presumes reset() precedes every episode
+    g.flags[v] = E::outcome(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
+    if (track_ret) g.ret[v] = fadd(g.ret[v], g.reward[v]);
+    E::obs(g.st[v], g.obs[v]);
+    if constexpr (WANT_FINAL) {
+#pragma unroll
+      for (int c = 0; c < E::OD; ++c) g.fin[v][c] = g.obs[v][c];
+    }
+    if constexpr (AUTO) {
+      const bool done = g.flags[v] != 0;
+      pending |= done ? (1u << v) : 0u;
+      if (count && done) {
+        acc.episodes += 1;
+        acc.terminated += (g.flags[v] & FLAG_TERMINATED) ? 1u : 0u;
+        acc.truncated += (g.flags[v] & FLAG_TRUNCATED) ? 1u : 0u;
+        acc.length_sum += g.steps[v];
+        acc.return_sum += (double)(E::ANALYTIC_RETURN ? E::episode_return(p.k, g.steps[v], g.flags[v]) : g.ret[v]);
       }
-      steps = 0;
-      ret = 0.0f;
-      E::obs(st, obs);
     }
   }
-  return flags;
+  if constexpr (AUTO) {
+    while (pending) {
+      const int sel = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const uint64_t gid = p.env_base + base + sel;
+      float ns[E::SD], no[E::OD];
+      if (p.reset_pool) {
+        const uint64_t j = (gid + t) % p.pool_len;
+#pragma unroll
+        for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
+      } else {
+        E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
+      }
+      E::obs(ns, no);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const bool hit = v == sel;
+#pragma unroll
+        for (int c = 0; c < E::SD; ++c) g.st[v][c] = hit ? ns[c] : g.st[v][c];
+#pragma unroll
+        for (int c = 0; c < E::OD; ++c) g.obs[v][c] = hit ? no[c] : g.obs[v][c];
+        g.steps[v] = hit ? 0u : g.steps[v];
+        g.ret[v] = hit ? 0.0f : g.ret[v];
+      }
+    }
+  }
 }
 
 template <int MODE>
@@ -183,7 +231,7 @@ struct CounterType<CNT_U16> {
 // Mode 1: per-call step kernel
 // =============================================================================================
 template <int KIND, int V, bool AUTO, int CNT>
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
@@ -196,67 +244,96 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ Kerne
 
   for (uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; grp < groups; grp += stride) {
     const uint64_t base = grp * V;
-    Vec<float, V> s[SD];
+    Group<KIND, V> g;
+    act_t action[V];
+    {
+      Vec<float, V> s[SD];
 #pragma unroll
-    for (int c = 0; c < SD; ++c) s[c] = ldv<float, V>(p.state + (uint64_t)c * p.n + base);
-    const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(p.actions) + base);
-    Vec<cnt_t, V> cnt;
-    if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
-    Vec<uint32_t, V> sb;
-    if constexpr (!AUTO && KIND == 0) sb = ldv<uint32_t, V>(p.sbt + base);
-    Vec<float, V> er;
-    if (track_ret) er = ldv<float, V>(p.ep_return + base);
-
-    Vec<float, V> o[OD], f[OD], rw;
-    Vec<uint8_t, V> fl;
+      for (int c = 0; c < SD; ++c) s[c] = ldv<float, V>(p.state + (uint64_t)c * p.n + base);
+      const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(p.actions) + base);
+      Vec<cnt_t, V> cnt;
+      if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
+      Vec<uint32_t, V> sb;
+      if constexpr (!AUTO && KIND == 0) sb = ldv<uint32_t, V>(p.sbt + base);
+      Vec<float, V> er;
+      if (track_ret) er = ldv<float, V>(p.ep_return + base);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float st[SD], obs[OD], fin[OD], reward;
+      for (int v = 0; v < V; ++v) {
 #pragma unroll
-      for (int c = 0; c < SD; ++c) st[c] = s[c].v[v];
-      uint32_t steps = 0, sbt = SBT_NONE;
-      if constexpr (CNT != CNT_NONE) steps = cnt.v[v];
-      if constexpr (!AUTO && KIND == 0) sbt = sb.v[v];
-      float ret = track_ret ? er.v[v] : 0.0f;
-      if constexpr (!E::CONTINUOUS) {
-        if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+        for (int c = 0; c < SD; ++c) g.st[v][c] = s[c].v[v];
+        action[v] = a.v[v];
+        g.steps[v] = 0;
+        g.sbt[v] = SBT_NONE;
+        if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+        if constexpr (!AUTO && KIND == 0) g.sbt[v] = sb.v[v];
+        g.ret[v] = track_ret ? er.v[v] : 0.0f;
+        if constexpr (!E::CONTINUOUS) {
+          if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+        }
       }
-      uint32_t flags;
-      if (want_final)
-        flags = env_transition<KIND, AUTO, true>(p, true, base + v, p.t, a.v[v], st, steps, sbt, ret, track_ret, reward,
-                                                 obs, fin, acc);
-      else
-        flags = env_transition<KIND, AUTO, false>(p, true, base + v, p.t, a.v[v], st, steps, sbt, ret, track_ret, reward,
-                                                  obs, fin, acc);
-#pragma unroll
-      for (int c = 0; c < SD; ++c) s[c].v[v] = st[c];
-#pragma unroll
-      for (int c = 0; c < OD; ++c) {
-        o[c].v[v] = obs[c];
-        f[c].v[v] = fin[c];
-      }
-      rw.v[v] = reward;
-      fl.v[v] = (uint8_t)flags;
-      if constexpr (CNT != CNT_NONE) cnt.v[v] = (cnt_t)steps;
-      if constexpr (!AUTO && KIND == 0) sb.v[v] = sbt;
-      if (track_ret) er.v[v] = ret;
     }
+    if (want_final)
+      step_group<KIND, V, AUTO, true>(p, true, base, p.t, action, track_ret, g, acc);
+    else
+      step_group<KIND, V, AUTO, false>(p, true, base, p.t, action, track_ret, g, acc);
 
+    {
+      Vec<float, V> s[SD];
 #pragma unroll
-    for (int c = 0; c < SD; ++c) stv<float, V>(p.state + (uint64_t)c * p.n + base, s[c]);
-    if constexpr (CNT != CNT_NONE) stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
-    if constexpr (!AUTO && KIND == 0) stv<uint32_t, V>(p.sbt + base, sb);
-    if (track_ret) stv<float, V>(p.ep_return + base, er);
+      for (int c = 0; c < SD; ++c) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[c].v[v] = g.st[v][c];
+        stv<float, V>(p.state + (uint64_t)c * p.n + base, s[c]);
+      }
+    }
+    if constexpr (CNT != CNT_NONE) {
+      Vec<cnt_t, V> cnt;
+#pragma unroll
+      for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
+      stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
+    }
+    if constexpr (!AUTO && KIND == 0) {
+      Vec<uint32_t, V> sb;
+#pragma unroll
+      for (int v = 0; v < V; ++v) sb.v[v] = g.sbt[v];
+      stv<uint32_t, V>(p.sbt + base, sb);
+    }
+    if (track_ret) {
+      Vec<float, V> er;
+#pragma unroll
+      for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
+      stv<float, V>(p.ep_return + base, er);
+    }
     if (p.obs_out) {
 #pragma unroll
-      for (int c = 0; c < OD; ++c) stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o[c]);
+      for (int c = 0; c < OD; ++c) {
+        Vec<float, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = g.obs[v][c];
+        stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+      }
     }
     if (want_final) {
 #pragma unroll
-      for (int c = 0; c < OD; ++c) stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, f[c]);
+      for (int c = 0; c < OD; ++c) {
+        Vec<float, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
+        stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+      }
     }
-    if (p.reward_out) stv<float, V>(p.reward_out + base, rw);
-    if (p.flags_out) stv<uint8_t, V>(p.flags_out + base, fl);
+    if (p.reward_out) {
+      Vec<float, V> rw;
+#pragma unroll
+      for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
+      stv<float, V>(p.reward_out + base, rw);
+    }
+    if (p.flags_out) {
+      Vec<uint8_t, V> fl;
+#pragma unroll
+      for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
+      stv<uint8_t, V>(p.flags_out + base, fl);
+    }
   }
   if constexpr (AUTO) stats_flush(acc, p);
 }
@@ -265,7 +342,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ Kerne
 // Mode 2: fused K-step rollout kernel
 // =============================================================================================
 template <int KIND, int V, bool AUTO, int CNT>
-__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) rollout_kernel(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
@@ -284,42 +361,37 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ke
     const uint64_t grp = grp0 + lane;
     const bool active = grp < groups;
     const uint64_t base = active ? grp * V : 0;
-    float st[V][SD];
-    uint32_t steps[V], sbt[V];
-    float ret[V];
+    Group<KIND, V> g;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      steps[v] = 0;
-      sbt[v] = SBT_NONE;
-      ret[v] = 0.0f;
+      g.steps[v] = 0;
+      g.sbt[v] = SBT_NONE;
+      g.ret[v] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < SD; ++c) g.st[v][c] = 0.0f;
     }
     if (active) {
 #pragma unroll
       for (int c = 0; c < SD; ++c) {
         const Vec<float, V> s = ldv<float, V>(p.state + (uint64_t)c * p.n + base);
 #pragma unroll
-        for (int v = 0; v < V; ++v) st[v][c] = s.v[v];
+        for (int v = 0; v < V; ++v) g.st[v][c] = s.v[v];
       }
       if constexpr (CNT != CNT_NONE) {
         const Vec<cnt_t, V> cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
 #pragma unroll
-        for (int v = 0; v < V; ++v) steps[v] = cnt.v[v];
+        for (int v = 0; v < V; ++v) g.steps[v] = cnt.v[v];
       }
       if constexpr (!AUTO && KIND == 0) {
         const Vec<uint32_t, V> sb = ldv<uint32_t, V>(p.sbt + base);
 #pragma unroll
-        for (int v = 0; v < V; ++v) sbt[v] = sb.v[v];
+        for (int v = 0; v < V; ++v) g.sbt[v] = sb.v[v];
       }
       if (track_ret) {
         const Vec<float, V> er = ldv<float, V>(p.ep_return + base);
 #pragma unroll
-        for (int v = 0; v < V; ++v) ret[v] = er.v[v];
+        for (int v = 0; v < V; ++v) g.ret[v] = er.v[v];
       }
-    } else {
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int c = 0; c < SD; ++c) st[v][c] = 0.0f;
     }
 
     Vec<act_t, V> a_next;
@@ -329,49 +401,61 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ke
 
     for (uint32_t kk = 0; kk < p.K; ++kk) {
       const uint64_t t = p.t + kk;
-      Vec<act_t, V> a = a_next;
+      act_t action[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) action[v] = a_next.v[v];
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
         if constexpr (V == 4) {
           const uint4 w = philox_env(p.seed, (p.env_base + base) >> 2, t, TAG_ACTION);
-          a.v[0] = action_from_word<KIND>(w.x);
-          a.v[1] = action_from_word<KIND>(w.y);
-          a.v[2] = action_from_word<KIND>(w.z);
-          a.v[3] = action_from_word<KIND>(w.w);
+          action[0] = action_from_word<KIND>(w.x);
+          action[1] = action_from_word<KIND>(w.y);
+          action[2] = action_from_word<KIND>(w.z);
+          action[3] = action_from_word<KIND>(w.w);
         } else {
-          const uint64_t g = p.env_base + base;
-          const uint4 w = philox_env(p.seed, g >> 2, t, TAG_ACTION);
-          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-          a.v[0] = action_from_word<KIND>(ws[g & 3]);
+          const uint64_t gid = p.env_base + base;
+          const uint4 w = philox_env(p.seed, gid >> 2, t, TAG_ACTION);
+          const uint32_t lane_word = (gid & 2) ? ((gid & 1) ? w.w : w.z) : ((gid & 1) ? w.y : w.x);
+          action[0] = action_from_word<KIND>(lane_word);
         }
       } else if (active && kk + 1 < p.K) {
         a_next = ldv<act_t, V>(actions + (uint64_t)(kk + 1) * p.n + base);  // prefetch next step
       }
-
-      Vec<float, V> o[OD], rw;
-      Vec<uint8_t, V> fl;
+      if constexpr (!E::CONTINUOUS) {
+        if (p.bad_action) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float obs[OD], fin[OD], reward;
-        if constexpr (!E::CONTINUOUS) {
-          if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+          for (int v = 0; v < V; ++v)
+            if (action[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
         }
-        const uint32_t flags = env_transition<KIND, AUTO, false>(p, active, base + v, t, a.v[v], st[v], steps[v], sbt[v],
-                                                                 ret[v], track_ret, reward, obs, fin, acc);
-#pragma unroll
-        for (int c = 0; c < OD; ++c) o[c].v[v] = obs[c];
-        rw.v[v] = reward;
-        fl.v[v] = (uint8_t)flags;
-        warp_dones += __popc(__ballot_sync(0xffffffffu, active && flags != 0));
       }
+
+      step_group<KIND, V, AUTO, false>(p, active, base, t, action, track_ret, g, acc);
+
+#pragma unroll
+      for (int v = 0; v < V; ++v) warp_dones += __popc(__ballot_sync(0xffffffffu, active && g.flags[v] != 0));
       if (active) {
         if (p.obs_out) {
           float* ob = p.obs_out + (uint64_t)kk * OD * p.n + base;
 #pragma unroll
-          for (int c = 0; c < OD; ++c) stv<float, V>(ob + (uint64_t)c * p.n, o[c]);
+          for (int c = 0; c < OD; ++c) {
+            Vec<float, V> o;
+#pragma unroll
+            for (int v = 0; v < V; ++v) o.v[v] = g.obs[v][c];
+            stv<float, V>(ob + (uint64_t)c * p.n, o);
+          }
         }
-        if (p.reward_out) stv<float, V>(p.reward_out + (uint64_t)kk * p.n + base, rw);
-        if (p.flags_out) stv<uint8_t, V>(p.flags_out + (uint64_t)kk * p.n + base, fl);
+        if (p.reward_out) {
+          Vec<float, V> rw;
+#pragma unroll
+          for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
+          stv<float, V>(p.reward_out + (uint64_t)kk * p.n + base, rw);
+        }
+        if (p.flags_out) {
+          Vec<uint8_t, V> fl;
+#pragma unroll
+          for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
+          stv<uint8_t, V>(p.flags_out + (uint64_t)kk * p.n + base, fl);
+        }
       }
     }
 
@@ -380,25 +464,25 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ke
       for (int c = 0; c < SD; ++c) {
         Vec<float, V> s;
 #pragma unroll
-        for (int v = 0; v < V; ++v) s.v[v] = st[v][c];
+        for (int v = 0; v < V; ++v) s.v[v] = g.st[v][c];
         stv<float, V>(p.state + (uint64_t)c * p.n + base, s);
       }
       if constexpr (CNT != CNT_NONE) {
         Vec<cnt_t, V> cnt;
 #pragma unroll
-        for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)steps[v];
+        for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
         stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
       }
       if constexpr (!AUTO && KIND == 0) {
         Vec<uint32_t, V> sb;
 #pragma unroll
-        for (int v = 0; v < V; ++v) sb.v[v] = sbt[v];
+        for (int v = 0; v < V; ++v) sb.v[v] = g.sbt[v];
         stv<uint32_t, V>(p.sbt + base, sb);
       }
       if (track_ret) {
         Vec<float, V> er;
 #pragma unroll
-        for (int v = 0; v < V; ++v) er.v[v] = ret[v];
+        for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
         stv<float, V>(p.ep_return + base, er);
       }
     }
@@ -498,6 +582,67 @@ __global__ void trig_probe_kernel(const float* x, float* s, float* c, float* s_o
   c[i] = cv;
   s_only[i] = sin_ref(x[i]);
   c_only[i] = cos_ref(x[i]);
+}
+
+// fast forms vs reference forms, counted on the device (tests/test_gpu_fastpath.py)
+//   mode 0: fdiv_const_fast(x, c, rc) vs __fdiv_rn(x, c) for every bit pattern x in [first, first+n) with div_safe(x)
+//   mode 1: sincos_small vs sincos_ref for every bit pattern with abstop12 < 0x3f4
+//   mode 2: cos_fast vs cos_ref for every bit pattern with abstop12 < 0x42f
+__global__ void fast_exhaustive_kernel(int mode, uint64_t first, uint64_t n, float c, float rc,
+                                       unsigned long long* checked, unsigned long long* bad, uint32_t* first_bad) {
+  unsigned long long my_checked = 0, my_bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = (uint32_t)(first + i);
+    const float x = __uint_as_float(u);
+    bool mismatch = false, applicable = false;
+    if (mode == 0) {
+      applicable = div_safe(x);
+      if (applicable) mismatch = __float_as_uint(fdiv_const_fast(x, c, rc)) != __float_as_uint(__fdiv_rn(x, c));
+    } else if (mode == 1) {
+      applicable = abstop12(x) < 0x3f4;
+      if (applicable) {
+        float s0, c0, s1, c1;
+        sincos_small(x, s0, c0);
+        sincos_ref(x, s1, c1);
+        mismatch = __float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1);
+      }
+    } else {
+      applicable = abstop12(x) < 0x42f;
+      if (applicable) mismatch = __float_as_uint(cos_fast(x)) != __float_as_uint(cos_ref(x));
+    }
+    my_checked += applicable ? 1 : 0;
+    if (mismatch) {
+      my_bad += 1;
+      atomicMin(first_bad, u);
+    }
+  }
+  atomicAdd(checked, my_checked);
+  if (my_bad) atomicAdd(bad, my_bad);
+}
+
+// fdiv_fast(a, b) vs __fdiv_rn(a, b) on pairs drawn from Philox, exponents spread over the safe range
+__global__ void fast_div_random_kernel(uint64_t seed, uint64_t n, unsigned long long* checked, unsigned long long* bad) {
+  unsigned long long my_checked = 0, my_bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 w = philox_env(seed, i, 0, 7u);
+    const uint32_t pats[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float a = __uint_as_float(pats[2 * j]), b = __uint_as_float(pats[2 * j + 1]);
+      // also the CartPole-shaped pair: any numerator over a denominator in [0.62, 0.67]
+      const float b2 = 0.62f + 0.05f * ((pats[2 * j + 1] >> 8) * 0x1p-24f);
+      if (div_safe(a) && div_safe(b)) {
+        my_checked++;
+        my_bad += __float_as_uint(fdiv_fast(a, b)) != __float_as_uint(__fdiv_rn(a, b));
+      }
+      if (div_safe(a)) {
+        my_checked++;
+        my_bad += __float_as_uint(fdiv_fast(a, b2)) != __float_as_uint(__fdiv_rn(a, b2));
+      }
+    }
+  }
+  atomicAdd(checked, my_checked);
+  if (my_bad) atomicAdd(bad, my_bad);
 }
 
 __global__ void philox_probe_kernel(const uint32_t* ctr_key, uint32_t* out, uint64_t n) {
