@@ -186,11 +186,56 @@ int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, u
   return MGYM_OK;
 }
 
+// TMA-staged step kernel (auto-reset, vector path, N a multiple of the 128-env warp tile)
+template <int KIND, int CNT>
+int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
+  using L = TmaLayout<KIND, CNT>;
+  auto kernel = step_kernel_tma<KIND, CNT>;
+  constexpr int threads = 256;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    MGYM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
+    configured = true;
+  }
+  int per_sm = 0;
+  MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, L::SMEM_BYTES));
+  if (per_sm < 1) per_sm = 1;
+  if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
+  uint64_t blocks = (uint64_t)e->num_sms * per_sm;
+  const uint64_t need = (p.n / TMA_TILE + 7) / 8;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  kernel<<<(unsigned)blocks, threads, L::SMEM_BYTES, st>>>(p);
+  MGYM_CUDA(cudaGetLastError());
+  return MGYM_OK;
+}
+
+bool use_tma() {
+  static bool v = [] {
+    const char* s = getenv("MGYM_NO_TMA");
+    return !(s && atoi(s) != 0);
+  }();
+  return v;
+}
+
 // kind x vector width x auto/manual x counter width
 template <int KIND, int V, bool ROLLOUT>
 int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   const uint64_t groups = p.n / V;
   const bool autor = e->cfg.auto_reset != 0;
+  if constexpr (!ROLLOUT && V == 4) {
+    if (autor && use_tma() && p.n % TMA_TILE == 0) {
+      if constexpr (KIND == 0) {
+        return launch_step_tma<KIND, CNT_U16>(e, p, st);
+      } else {
+        switch (e->cnt_mode) {
+          case CNT_NONE: return launch_step_tma<KIND, CNT_NONE>(e, p, st);
+          case CNT_U16: return launch_step_tma<KIND, CNT_U16>(e, p, st);
+          default: return launch_step_tma<KIND, CNT_U32>(e, p, st);
+        }
+      }
+    }
+  }
 #define MGYM_LAUNCH(AUTO_, CNT_)                                                                         \
   do {                                                                                                   \
     if constexpr (ROLLOUT)                                                                               \

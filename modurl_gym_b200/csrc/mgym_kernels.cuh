@@ -87,10 +87,26 @@ __device__ __forceinline__ void stv(T* p, const Vec<T, V>& r) {
 struct StatAcc {
   uint32_t episodes = 0, terminated = 0, truncated = 0;
   unsigned long long length_sum = 0;
-  double return_sum = 0.0;
+  double return_sum = 0.0;  // only kinds without an analytic return accumulate here
   unsigned long long done_steps = 0;
 };
 
+// Sum of episode returns from the integer sums, for kinds whose rewards are constants.
+template <int KIND>
+__device__ __forceinline__ double analytic_return_sum(const EnvConsts& k, double episodes, double terminated,
+                                                      double truncated, double length_sum) {
+  if constexpr (KIND == 0) {  // cartpole.rs:310-347: +1 per step; sutton_barto: -1 on the fall, +1 on truncation
+    return k.sutton_barto ? (truncated - terminated) : length_sum;
+  } else if constexpr (KIND == 1) {  // mountain_car.rs:319: -1 per step
+    return -length_sum;
+  } else if constexpr (KIND == 4) {  // Acrobot: -1 per step, 0 on the terminating step
+    return terminated - length_sum;
+  } else {
+    return 0.0 * episodes;
+  }
+}
+
+template <int KIND>
 __device__ __forceinline__ void stats_flush(const StatAcc& a, const KernelParams& p) {
   __shared__ unsigned long long sh_u[5];
   __shared__ double sh_d;
@@ -125,7 +141,11 @@ __device__ __forceinline__ void stats_flush(const StatAcc& a, const KernelParams
       atomicAdd(&p.stats[1], sh_u[1]);
       atomicAdd(&p.stats[2], sh_u[2]);
       atomicAdd(&p.stats[3], sh_u[3]);
-      atomicAdd(reinterpret_cast<double*>(&p.stats[4]), sh_d);
+      const double ret = Env<KIND>::ANALYTIC_RETURN
+                             ? analytic_return_sum<KIND>(p.k, (double)sh_u[0], (double)sh_u[1], (double)sh_u[2],
+                                                         (double)sh_u[3])
+                             : sh_d;
+      atomicAdd(reinterpret_cast<double*>(&p.stats[4]), ret);
     }
     if (p.done_count && sh_u[4]) atomicAdd(p.done_count, sh_u[4]);
   }
@@ -173,20 +193,23 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
     if constexpr (AUTO) g.sbt[v] = SBT_NONE;  // auto-reset presumes reset() precedes every episode
     g.flags[v] = E::outcome(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
     if (track_ret) g.ret[v] = fadd(g.ret[v], g.reward[v]);
-    E::obs(g.st[v], g.obs[v]);
-    if constexpr (WANT_FINAL) {
+    if constexpr (!E::OBS_IS_STATE || WANT_FINAL) {
+      E::obs(g.st[v], g.obs[v]);
+      if constexpr (WANT_FINAL) {
 #pragma unroll
-      for (int c = 0; c < E::OD; ++c) g.fin[v][c] = g.obs[v][c];
+        for (int c = 0; c < E::OD; ++c) g.fin[v][c] = g.obs[v][c];
+      }
     }
     if constexpr (AUTO) {
       const bool done = g.flags[v] != 0;
       pending |= done ? (1u << v) : 0u;
-      if (count && done) {
-        acc.episodes += 1;
-        acc.terminated += (g.flags[v] & FLAG_TERMINATED) ? 1u : 0u;
-        acc.truncated += (g.flags[v] & FLAG_TRUNCATED) ? 1u : 0u;
-        acc.length_sum += g.steps[v];
-        acc.return_sum += (double)(E::ANALYTIC_RETURN ? E::episode_return(p.k, g.steps[v], g.flags[v]) : g.ret[v]);
+      const bool tally = count && done;
+      acc.episodes += tally ? 1u : 0u;
+      acc.terminated += tally ? (g.flags[v] & FLAG_TERMINATED) : 0u;
+      acc.truncated += tally ? ((g.flags[v] & FLAG_TRUNCATED) >> 1) : 0u;
+      acc.length_sum += tally ? g.steps[v] : 0u;
+      if constexpr (!E::ANALYTIC_RETURN) {
+        if (tally) acc.return_sum += (double)g.ret[v];
       }
     }
   }
@@ -203,14 +226,16 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
       } else {
         E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
       }
-      E::obs(ns, no);
+      if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const bool hit = v == sel;
 #pragma unroll
         for (int c = 0; c < E::SD; ++c) g.st[v][c] = hit ? ns[c] : g.st[v][c];
+        if constexpr (!E::OBS_IS_STATE) {
 #pragma unroll
-        for (int c = 0; c < E::OD; ++c) g.obs[v][c] = hit ? no[c] : g.obs[v][c];
+          for (int c = 0; c < E::OD; ++c) g.obs[v][c] = hit ? no[c] : g.obs[v][c];
+        }
         g.steps[v] = hit ? 0u : g.steps[v];
         g.ret[v] = hit ? 0.0f : g.ret[v];
       }
@@ -309,7 +334,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
       for (int c = 0; c < OD; ++c) {
         Vec<float, V> o;
 #pragma unroll
-        for (int v = 0; v < V; ++v) o.v[v] = g.obs[v][c];
+        for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
         stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
       }
     }
@@ -335,7 +360,215 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
       stv<uint8_t, V>(p.flags_out + base, fl);
     }
   }
-  if constexpr (AUTO) stats_flush(acc, p);
+  if constexpr (AUTO) stats_flush<KIND>(acc, p);
+}
+
+// =============================================================================================
+// Mode 1, TMA-staged: the same step, with the inputs of each warp's next tiles already in flight.
+//
+// The LDG form above can only keep (resident warps x 76 B x 32 lanes) of reads in flight, and the
+// register budget of the interleaved 4-env arithmetic caps resident warps at 16-32 per SM -- not
+// enough bytes in flight to cover HBM latency (ncu: long-scoreboard stalls at the loads, DRAM < 50 %).
+// Here every warp owns a ring of STAGES shared-memory tiles (128 envs each: SD state rows, actions,
+// counters) that one elected lane fills with cp.async.bulk (TMA, 1-D bulk copies completing on an
+// mbarrier).  Bytes in flight no longer depend on occupancy: warps x STAGES x ~2.4 KB per SM.
+// =============================================================================================
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+}  // namespace tma
+
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_TILE = 128;  // envs per warp tile: 32 lanes x V=4
+
+template <int KIND, int CNT>
+struct TmaLayout {
+  using E = Env<KIND>;
+  static constexpr uint32_t ROW = TMA_TILE * 4;  // one f32 row of a tile
+  static constexpr uint32_t OFF_ACT = E::SD * ROW;
+  static constexpr uint32_t ACT_BYTES = TMA_TILE * sizeof(typename E::act_t);
+  static constexpr uint32_t OFF_CNT = OFF_ACT + ACT_BYTES;
+  static constexpr uint32_t CNT_BYTES = CNT == CNT_NONE ? 0 : TMA_TILE * sizeof(typename CounterType<CNT>::type);
+  static constexpr uint32_t OFF_RET = OFF_CNT + CNT_BYTES;
+  static constexpr uint32_t RET_BYTES = E::ANALYTIC_RETURN ? 0 : ROW;
+  static constexpr uint32_t STAGE_BYTES = (OFF_RET + RET_BYTES + 127u) & ~127u;
+  static constexpr uint32_t BAR_BYTES = 8 * TMA_STAGES * 8;  // 8 warps x STAGES mbarriers
+  static constexpr uint32_t SMEM_BYTES = 128 + BAR_BYTES + 8 * TMA_STAGES * STAGE_BYTES;
+};
+
+template <int KIND, int CNT>
+__global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel_tma(const __grid_constant__ KernelParams p) {
+  using E = Env<KIND>;
+  using L = TmaLayout<KIND, CNT>;
+  using act_t = typename E::act_t;
+  using cnt_t = typename CounterType<CNT>::type;
+  constexpr int SD = E::SD, OD = E::OD, V = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + warp * TMA_STAGES * 8;
+  const uint32_t data0 = smem_base + L::BAR_BYTES + warp * TMA_STAGES * L::STAGE_BYTES;
+  const uint64_t n_tiles = p.n / TMA_TILE;
+  const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const uint64_t gw_stride = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
+  const bool want_final = p.final_obs_out != nullptr;
+  const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
+  StatAcc acc;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_STAGES; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+
+  // lane 0: arm the stage's mbarrier with the byte count, then launch the bulk copies of one tile
+  auto issue = [&](uint64_t tile, uint32_t s) {
+    const uint32_t bar = bar0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
+    const uint64_t e0 = tile * TMA_TILE;
+    tma::mbar_expect_tx(bar, SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u));
+#pragma unroll
+    for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar);
+    tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
+    if constexpr (CNT != CNT_NONE)
+      tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
+    if constexpr (!E::ANALYTIC_RETURN) {
+      if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
+    }
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_STAGES; ++s) {
+      const uint64_t tile = gw + (uint64_t)s * gw_stride;
+      if (tile < n_tiles) issue(tile, s);
+    }
+  }
+
+  uint32_t it = 0;
+  for (uint64_t tile = gw; tile < n_tiles; tile += gw_stride, ++it) {
+    const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
+    const uint64_t base = tile * TMA_TILE + lane * V;
+    tma::mbar_wait(bar0 + 8 * s, parity);
+
+    Group<KIND, V> g;
+    act_t action[V];
+    {
+      const uint8_t* st = smem_raw + (data0 + s * L::STAGE_BYTES - tma::smem_u32(smem_raw));
+      Vec<float, V> row[SD];
+#pragma unroll
+      for (int c = 0; c < SD; ++c) row[c] = ldv<float, V>(reinterpret_cast<const float*>(st + c * L::ROW) + lane * V);
+      const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(st + L::OFF_ACT) + lane * V);
+      Vec<cnt_t, V> cnt;
+      if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + lane * V);
+      Vec<float, V> er;
+      if constexpr (!E::ANALYTIC_RETURN) {
+        if (track_ret) er = ldv<float, V>(reinterpret_cast<const float*>(st + L::OFF_RET) + lane * V);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int c = 0; c < SD; ++c) g.st[v][c] = row[c].v[v];
+        action[v] = a.v[v];
+        g.steps[v] = 0;
+        g.sbt[v] = SBT_NONE;
+        if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+        g.ret[v] = 0.0f;
+        if constexpr (!E::ANALYTIC_RETURN) g.ret[v] = track_ret ? er.v[v] : 0.0f;
+        if constexpr (!E::CONTINUOUS) {
+          if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+        }
+      }
+    }
+    __syncwarp();  // every lane has taken its values out of the stage: it may be refilled
+    if (lane == 0) {
+      const uint64_t next = tile + (uint64_t)TMA_STAGES * gw_stride;
+      if (next < n_tiles) issue(next, s);
+    }
+
+    if (want_final)
+      step_group<KIND, V, true, true>(p, true, base, p.t, action, track_ret, g, acc);
+    else
+      step_group<KIND, V, true, false>(p, true, base, p.t, action, track_ret, g, acc);
+
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+      Vec<float, V> o;
+#pragma unroll
+      for (int v = 0; v < V; ++v) o.v[v] = g.st[v][c];
+      stv<float, V>(p.state + (uint64_t)c * p.n + base, o);
+    }
+    if constexpr (CNT != CNT_NONE) {
+      Vec<cnt_t, V> cnt;
+#pragma unroll
+      for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
+      stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
+    }
+    if constexpr (!E::ANALYTIC_RETURN) {
+      if (track_ret) {
+        Vec<float, V> er;
+#pragma unroll
+        for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
+        stv<float, V>(p.ep_return + base, er);
+      }
+    }
+    if (p.obs_out) {
+#pragma unroll
+      for (int c = 0; c < OD; ++c) {
+        Vec<float, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
+        stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+      }
+    }
+    if (want_final) {
+#pragma unroll
+      for (int c = 0; c < OD; ++c) {
+        Vec<float, V> o;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
+        stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+      }
+    }
+    if (p.reward_out) {
+      Vec<float, V> rw;
+#pragma unroll
+      for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
+      stv<float, V>(p.reward_out + base, rw);
+    }
+    if (p.flags_out) {
+      Vec<uint8_t, V> fl;
+#pragma unroll
+      for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
+      stv<uint8_t, V>(p.flags_out + base, fl);
+    }
+  }
+  stats_flush<KIND>(acc, p);
 }
 
 // =============================================================================================
@@ -440,7 +673,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) rollout_kernel(const __g
           for (int c = 0; c < OD; ++c) {
             Vec<float, V> o;
 #pragma unroll
-            for (int v = 0; v < V; ++v) o.v[v] = g.obs[v][c];
+            for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
             stv<float, V>(ob + (uint64_t)c * p.n, o);
           }
         }
@@ -488,7 +721,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) rollout_kernel(const __g
     }
   }
   if (lane == 0) acc.done_steps = warp_dones;
-  stats_flush(acc, p);
+  stats_flush<KIND>(acc, p);
 }
 
 // =============================================================================================
