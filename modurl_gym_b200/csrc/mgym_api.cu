@@ -191,7 +191,7 @@ template <int KIND, int CNT>
 int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   using L = TmaLayout<KIND, CNT>;
   auto kernel = step_kernel_tma<KIND, CNT>;
-  constexpr int threads = 256;
+  constexpr int threads = TMA_THREADS;
   static bool configured = false;  // per instantiation
   if (!configured) {
     MGYM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
@@ -202,7 +202,7 @@ int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
   uint64_t blocks = (uint64_t)e->num_sms * per_sm;
-  const uint64_t need = (p.n / TMA_TILE + 7) / 8;
+  const uint64_t need = p.n / TMA_TILE;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   kernel<<<(unsigned)blocks, threads, L::SMEM_BYTES, st>>>(p);

@@ -15,6 +15,9 @@
 #ifndef MGYM_MIN_BLOCKS
 #define MGYM_MIN_BLOCKS 1
 #endif
+#ifndef MGYM_TMA_MIN_BLOCKS
+#define MGYM_TMA_MIN_BLOCKS 2
+#endif
 
 namespace mgym {
 
@@ -369,9 +372,9 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
 // The LDG form above can only keep (resident warps x 76 B x 32 lanes) of reads in flight, and the
 // register budget of the interleaved 4-env arithmetic caps resident warps at 16-32 per SM -- not
 // enough bytes in flight to cover HBM latency (ncu: long-scoreboard stalls at the loads, DRAM < 50 %).
-// Here every warp owns a ring of STAGES shared-memory tiles (128 envs each: SD state rows, actions,
-// counters) that one elected lane fills with cp.async.bulk (TMA, 1-D bulk copies completing on an
-// mbarrier).  Bytes in flight no longer depend on occupancy: warps x STAGES x ~2.4 KB per SM.
+// Here every CTA owns a ring of STAGES shared-memory tiles (1024 envs each: SD state rows, actions,
+// counters, ~19 KB) that a dedicated producer warp fills with cp.async.bulk (TMA, 1-D bulk copies
+// completing on an mbarrier).  Bytes in flight no longer depend on occupancy: CTAs x STAGES x 19 KB.
 // =============================================================================================
 namespace tma {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -386,6 +389,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -403,7 +409,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }  // namespace tma
 
 constexpr int TMA_STAGES = 4;
-constexpr int TMA_TILE = 128;  // envs per warp tile: 32 lanes x V=4
+constexpr int TMA_CONSUMER_WARPS = 8;
+constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 1) * 32;  // + one producer warp
+constexpr int TMA_TILE = TMA_CONSUMER_WARPS * 32 * 4;       // envs per CTA tile: 256 consumer threads x V=4
 
 template <int KIND, int CNT>
 struct TmaLayout {
@@ -416,12 +424,16 @@ struct TmaLayout {
   static constexpr uint32_t OFF_RET = OFF_CNT + CNT_BYTES;
   static constexpr uint32_t RET_BYTES = E::ANALYTIC_RETURN ? 0 : ROW;
   static constexpr uint32_t STAGE_BYTES = (OFF_RET + RET_BYTES + 127u) & ~127u;
-  static constexpr uint32_t BAR_BYTES = 8 * TMA_STAGES * 8;  // 8 warps x STAGES mbarriers
-  static constexpr uint32_t SMEM_BYTES = 128 + BAR_BYTES + 8 * TMA_STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES]
+  static constexpr uint32_t SMEM_BYTES = 128 + BAR_BYTES + TMA_STAGES * STAGE_BYTES;
 };
 
+// Warp-specialised: warp 8 is the TMA producer (one elected lane arms full[s] and launches the six
+// bulk copies of a 1024-env tile once the consumers have released stage s through empty[s]); warps
+// 0-7 are consumers (wait full[s], pull their 4 envs out of shared memory, release the stage, step,
+// store straight from registers).
 template <int KIND, int CNT>
-__global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel_tma(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_tma(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
   using L = TmaLayout<KIND, CNT>;
   using act_t = typename E::act_t;
@@ -429,143 +441,145 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel_tma(const __
   constexpr int SD = E::SD, OD = E::OD, V = 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar0 = smem_base + warp * TMA_STAGES * 8;
-  const uint32_t data0 = smem_base + L::BAR_BYTES + warp * TMA_STAGES * L::STAGE_BYTES;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_base, empty0 = smem_base + 8 * TMA_STAGES;
+  const uint32_t data0 = smem_base + L::BAR_BYTES;
   const uint64_t n_tiles = p.n / TMA_TILE;
-  const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  const uint64_t gw_stride = (uint64_t)gridDim.x * (blockDim.x >> 5);
   const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
   const bool want_final = p.final_obs_out != nullptr;
-  const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
   StatAcc acc;
 
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < TMA_STAGES; ++s) tma::mbar_init(bar0 + 8 * s, 1);
-    tma::fence_mbar_init();
-  }
-  __syncwarp();
-
-  // lane 0: arm the stage's mbarrier with the byte count, then launch the bulk copies of one tile
-  auto issue = [&](uint64_t tile, uint32_t s) {
-    const uint32_t bar = bar0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
-    const uint64_t e0 = tile * TMA_TILE;
-    tma::mbar_expect_tx(bar, SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u));
-#pragma unroll
-    for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar);
-    tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
-    if constexpr (CNT != CNT_NONE)
-      tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
-    if constexpr (!E::ANALYTIC_RETURN) {
-      if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
-    }
-  };
-
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < TMA_STAGES; ++s) {
-      const uint64_t tile = gw + (uint64_t)s * gw_stride;
-      if (tile < n_tiles) issue(tile, s);
+      tma::mbar_init(full0 + 8 * s, 1);
+      tma::mbar_init(empty0 + 8 * s, TMA_CONSUMER_WARPS);
     }
+    tma::fence_mbar_init();
   }
+  __syncthreads();
 
-  uint32_t it = 0;
-  for (uint64_t tile = gw; tile < n_tiles; tile += gw_stride, ++it) {
-    const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
-    const uint64_t base = tile * TMA_TILE + lane * V;
-    tma::mbar_wait(bar0 + 8 * s, parity);
-
-    Group<KIND, V> g;
-    act_t action[V];
-    {
-      const uint8_t* st = smem_raw + (data0 + s * L::STAGE_BYTES - tma::smem_u32(smem_raw));
-      Vec<float, V> row[SD];
+  if (warp == TMA_CONSUMER_WARPS) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
+      const uint32_t tx = SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u);
+      uint32_t it = 0;
+      for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
+        tma::mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);  // first round passes at once
+        const uint32_t bar = full0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
+        const uint64_t e0 = tile * TMA_TILE;
+        tma::mbar_expect_tx(bar, tx);
 #pragma unroll
-      for (int c = 0; c < SD; ++c) row[c] = ldv<float, V>(reinterpret_cast<const float*>(st + c * L::ROW) + lane * V);
-      const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(st + L::OFF_ACT) + lane * V);
-      Vec<cnt_t, V> cnt;
-      if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + lane * V);
-      Vec<float, V> er;
-      if constexpr (!E::ANALYTIC_RETURN) {
-        if (track_ret) er = ldv<float, V>(reinterpret_cast<const float*>(st + L::OFF_RET) + lane * V);
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-#pragma unroll
-        for (int c = 0; c < SD; ++c) g.st[v][c] = row[c].v[v];
-        action[v] = a.v[v];
-        g.steps[v] = 0;
-        g.sbt[v] = SBT_NONE;
-        if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
-        g.ret[v] = 0.0f;
-        if constexpr (!E::ANALYTIC_RETURN) g.ret[v] = track_ret ? er.v[v] : 0.0f;
-        if constexpr (!E::CONTINUOUS) {
-          if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+        for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar);
+        tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
+        if constexpr (CNT != CNT_NONE)
+          tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
+        if constexpr (!E::ANALYTIC_RETURN) {
+          if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
         }
       }
     }
-    __syncwarp();  // every lane has taken its values out of the stage: it may be refilled
-    if (lane == 0) {
-      const uint64_t next = tile + (uint64_t)TMA_STAGES * gw_stride;
-      if (next < n_tiles) issue(next, s);
-    }
+    __syncwarp();
+  } else {
+    // ---------------- consumers ----------------
+    const uint32_t tid = threadIdx.x;  // 0..255
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
+      const uint64_t base = tile * TMA_TILE + tid * V;
+      tma::mbar_wait(full0 + 8 * s, parity);
 
-    if (want_final)
-      step_group<KIND, V, true, true>(p, true, base, p.t, action, track_ret, g, acc);
-    else
-      step_group<KIND, V, true, false>(p, true, base, p.t, action, track_ret, g, acc);
-
+      Group<KIND, V> g;
+      act_t action[V];
+      {
+        const uint8_t* st = smem_raw + (data0 + s * L::STAGE_BYTES - tma::smem_u32(smem_raw));
+        Vec<float, V> row[SD];
 #pragma unroll
-    for (int c = 0; c < SD; ++c) {
-      Vec<float, V> o;
-#pragma unroll
-      for (int v = 0; v < V; ++v) o.v[v] = g.st[v][c];
-      stv<float, V>(p.state + (uint64_t)c * p.n + base, o);
-    }
-    if constexpr (CNT != CNT_NONE) {
-      Vec<cnt_t, V> cnt;
-#pragma unroll
-      for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
-      stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
-    }
-    if constexpr (!E::ANALYTIC_RETURN) {
-      if (track_ret) {
+        for (int c = 0; c < SD; ++c) row[c] = ldv<float, V>(reinterpret_cast<const float*>(st + c * L::ROW) + tid * V);
+        const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(st + L::OFF_ACT) + tid * V);
+        Vec<cnt_t, V> cnt;
+        if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + tid * V);
         Vec<float, V> er;
+        if constexpr (!E::ANALYTIC_RETURN) {
+          if (track_ret) er = ldv<float, V>(reinterpret_cast<const float*>(st + L::OFF_RET) + tid * V);
+        }
 #pragma unroll
-        for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
-        stv<float, V>(p.ep_return + base, er);
+        for (int v = 0; v < V; ++v) {
+#pragma unroll
+          for (int c = 0; c < SD; ++c) g.st[v][c] = row[c].v[v];
+          action[v] = a.v[v];
+          g.steps[v] = 0;
+          g.sbt[v] = SBT_NONE;
+          if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+          g.ret[v] = 0.0f;
+          if constexpr (!E::ANALYTIC_RETURN) g.ret[v] = track_ret ? er.v[v] : 0.0f;
+          if constexpr (!E::CONTINUOUS) {
+            if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
+          }
+        }
       }
-    }
-    if (p.obs_out) {
+      __syncwarp();  // every lane of this warp has its values in registers
+      if (lane == 0) tma::mbar_arrive(empty0 + 8 * s);
+
+      if (want_final)
+        step_group<KIND, V, true, true>(p, true, base, p.t, action, track_ret, g, acc);
+      else
+        step_group<KIND, V, true, false>(p, true, base, p.t, action, track_ret, g, acc);
+
 #pragma unroll
-      for (int c = 0; c < OD; ++c) {
+      for (int c = 0; c < SD; ++c) {
         Vec<float, V> o;
 #pragma unroll
-        for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-        stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+        for (int v = 0; v < V; ++v) o.v[v] = g.st[v][c];
+        stv<float, V>(p.state + (uint64_t)c * p.n + base, o);
       }
-    }
-    if (want_final) {
+      if constexpr (CNT != CNT_NONE) {
+        Vec<cnt_t, V> cnt;
 #pragma unroll
-      for (int c = 0; c < OD; ++c) {
-        Vec<float, V> o;
-#pragma unroll
-        for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
-        stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+        for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
+        stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
       }
-    }
-    if (p.reward_out) {
-      Vec<float, V> rw;
+      if constexpr (!E::ANALYTIC_RETURN) {
+        if (track_ret) {
+          Vec<float, V> er;
 #pragma unroll
-      for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
-      stv<float, V>(p.reward_out + base, rw);
-    }
-    if (p.flags_out) {
-      Vec<uint8_t, V> fl;
+          for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
+          stv<float, V>(p.ep_return + base, er);
+        }
+      }
+      if (p.obs_out) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
-      stv<uint8_t, V>(p.flags_out + base, fl);
+        for (int c = 0; c < OD; ++c) {
+          Vec<float, V> o;
+#pragma unroll
+          for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
+          stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+        }
+      }
+      if (want_final) {
+#pragma unroll
+        for (int c = 0; c < OD; ++c) {
+          Vec<float, V> o;
+#pragma unroll
+          for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
+          stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+        }
+      }
+      if (p.reward_out) {
+        Vec<float, V> rw;
+#pragma unroll
+        for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
+        stv<float, V>(p.reward_out + base, rw);
+      }
+      if (p.flags_out) {
+        Vec<uint8_t, V> fl;
+#pragma unroll
+        for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
+        stv<uint8_t, V>(p.flags_out + base, fl);
+      }
     }
   }
   stats_flush<KIND>(acc, p);
