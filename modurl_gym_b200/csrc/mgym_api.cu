@@ -138,6 +138,7 @@ EnvConsts make_consts(int kind, const mgym_config& cfg) {
   k.max_vel_1 = 4.0f * pi;
   k.max_vel_2 = 9.0f * pi;
 
+  k.one = 1.0f;
   k.is_euler = cfg.is_euler;
   k.sutton_barto = cfg.sutton_barto_reward;
   k.max_steps = (kind == MGYM_CARTPOLE_V1) ? 0 : cfg.max_episode_steps;

@@ -179,11 +179,20 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
   float aux[V];
   bool ok[V];
   bool all_ok = true;
+  if constexpr (E::HAS_PAIR && V % 2 == 0) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    aux[v] = 0.0f;
-    ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
-    all_ok = all_ok && ok[v];
+    for (int v = 0; v < V; v += 2) {
+      aux[v] = aux[v + 1] = 0.0f;
+      E::dynamics_fast2(g.st[v], g.st[v + 1], action[v], action[v + 1], p.k, ok[v], ok[v + 1]);
+      all_ok = all_ok && ok[v] && ok[v + 1];
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      aux[v] = 0.0f;
+      ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
+      all_ok = all_ok && ok[v];
+    }
   }
   if (!all_ok) {
 #pragma unroll
