@@ -34,11 +34,16 @@ NUM_ENVS_PER_GPU = 1 << 24
 BYTES_PER_ENV_STEP = 42
 
 
+def workload_name(n):
+    return (f"{KIND_NAME}, {n} envs per GPU, per-call step kernel with device-side auto-reset "
+            "(BASELINE.json configs[1])")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--num-envs", type=int, default=NUM_ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -133,7 +138,7 @@ def run_reference(args, rank):
     from oracle import oracle as o
 
     threads = os.cpu_count() or 1
-    S = 1 << 20
+    S = 1 << 18  # env-steps per thread per 'step': ~20 ms, so K=2000 still ends within a minute
     for _ in range(args.warmup):
         o.baseline_loop(o.CARTPOLE, S, threads, seed=0x5EED)
     t0 = time.perf_counter()
@@ -148,8 +153,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{KIND_NAME} step loop, CPU restatement of cartpole.rs:251-348 (oracle/ C port; "
-                               "the Rust crate cannot be built here: no cargo/rustc)", "sample": sample},
+        "config": {"workload": workload_name(args.num_envs), "num_envs_per_gpu": args.num_envs, "mode": "step",
+                   "arm": "CPU restatement of cartpole.rs:251-348 (oracle/ C port; the Rust crate cannot be built "
+                          "here: no cargo/rustc); each step is a bounded sample of the workload", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,8 +179,12 @@ def run_native(args, rank, local_rank, world):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
 
-    n = args.num_envs
-    env = m.GpuVecEnv(KIND_NAME, n, device=local_rank, seed=0x5EED, env_index_base=rank * n)
+    from modurl_gym_b200.distributed import max_over_ranks, shard_range
+
+    n = args.num_envs  # weak scaling: a fixed slice per GPU
+    begin, end = shard_range(n * world, rank, world)
+    assert end - begin == n
+    env = m.GpuVecEnv(KIND_NAME, n, device=local_rank, seed=0x5EED, env_index_base=begin)
     env.reset()
     # rotating pool of pre-generated random actions keeps RNG out of the timed kernel
     gen = torch.Generator(device=device)
@@ -212,10 +222,7 @@ def run_native(args, rank, local_rank, world):
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms, device)
     stats = env.all_reduce_stats()  # NCCL all-reduce of the episode statistics (5 doubles)
 
     # ---- end to end through the host-buffer entry point: H2D actions, step, D2H obs/reward/flags ----
@@ -232,10 +239,7 @@ def run_native(args, rank, local_rank, world):
         env.step_host(h_act, h_obs, h_rew, h_flg)
     e1.record()
     barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), device)
     h2d = h_act.numel() * h_act.element_size()
     d2h = sum(x.numel() * x.element_size() for x in (h_obs, h_rew, h_flg))
 
@@ -250,15 +254,14 @@ def run_native(args, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{KIND_NAME}, {n} envs per GPU, per-call step kernel with device-side auto-reset "
-                            "(BASELINE.json configs[1])",
+                "workload": workload_name(n),
                 "num_envs_per_gpu": n, "mode": "step", "obs": "zero-copy (obs aliases the resident state rows)",
                 "actions": "rotating pool of 16 pre-generated uint8[N] buffers",
                 "l2": f"working set {BYTES_PER_ENV_STEP * n / 1e6:.0f} MB per step > 126 MB L2 (inputs larger than L2)",
                 "parallelism": f"dp{world} (independent env slices, no data-path collective)",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "step_kernel<CartPole,V=4,auto,u16>",
+                         "traffic": None, "kernel": "step_kernel_tma<CartPole-v1, u16 counter>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
             "e2e": {"value": float(n) * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,

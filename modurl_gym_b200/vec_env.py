@@ -222,13 +222,9 @@ class GpuVecEnv:
 
     def all_reduce_stats(self, group=None):
         """Sum the episode statistics over all ranks (NCCL all-reduce of 5 doubles)."""
-        import torch.distributed as dist
+        from .distributed import all_reduce_stats_vector
 
-        vec = self.stats_tensor()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-        v = vec.tolist()
-        return EpisodeStats(int(v[0]), int(v[1]), int(v[2]), int(v[3]), v[4])
+        return EpisodeStats(*all_reduce_stats_vector(self.stats_tensor(), group))
 
 
 def _hptr(a):
