@@ -138,7 +138,7 @@ def run_reference(args, rank):
     from oracle import oracle as o
 
     threads = os.cpu_count() or 1
-    S = 1 << 18  # env-steps per thread per 'step': ~20 ms, so K=2000 still ends within a minute
+    S = 1 << 20  # env-steps per thread per 'step' (~80 ms): K=2000 ends within about three minutes
     for _ in range(args.warmup):
         o.baseline_loop(o.CARTPOLE, S, threads, seed=0x5EED)
     t0 = time.perf_counter()
