@@ -15,6 +15,9 @@
 #ifndef MGYM_MIN_BLOCKS
 #define MGYM_MIN_BLOCKS 1
 #endif
+#ifndef MGYM_ROLLOUT_MIN_BLOCKS
+#define MGYM_ROLLOUT_MIN_BLOCKS 2
+#endif
 #ifndef MGYM_TMA_MIN_BLOCKS
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 // Mode 2: fused K-step rollout kernel
 // =============================================================================================
 template <int KIND, int V, bool AUTO, int CNT>
-__global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) rollout_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
