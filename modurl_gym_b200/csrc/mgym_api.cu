@@ -139,6 +139,9 @@ EnvConsts make_consts(int kind, const mgym_config& cfg) {
   k.max_vel_2 = 9.0f * pi;
 
   k.one = 1.0f;
+  k.r_alive = cfg.sutton_barto_reward ? 0.0f : 1.0f;   // cartpole.rs:311
+  k.r_fell = cfg.sutton_barto_reward ? -1.0f : 1.0f;   // cartpole.rs:322
+  k.r_after = cfg.sutton_barto_reward ? -1.0f : 0.0f;  // cartpole.rs:338
   k.is_euler = cfg.is_euler;
   k.sutton_barto = cfg.sutton_barto_reward;
   k.max_steps = (kind == MGYM_CARTPOLE_V1) ? 0 : cfg.max_episode_steps;
@@ -157,6 +160,13 @@ KernelParams base_params(const mgym_env* e) {
   p.bad_action = e->cfg.validate_actions ? e->bad_action : nullptr;
   p.n = e->n;
   p.seed = e->seed;
+  {
+    uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+      p.keys.k[r][0] = k0, p.keys.k[r][1] = k1;
+      k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+  }
   p.env_base = e->cfg.env_index_base;
   p.t = e->t;
   p.k = e->k;
