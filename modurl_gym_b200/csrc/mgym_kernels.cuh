@@ -117,6 +117,26 @@ __device__ __forceinline__ void stv(T* p, const Vec<T, V>& r) {
   }
 }
 
+// ---- actions of V envs kept as the raw loaded word(s), unpacked only where they are used, so a
+// prefetched load can stay in flight across a whole rollout step -----------------------------------
+template <typename T, int V>
+struct RawActions {
+  Vec<T, V> v;
+  __device__ __forceinline__ void load(const T* p) { v = ldv<T, V>(p); }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v.v[i] = T(0);
+  }
+  __device__ __forceinline__ T get(int i) const { return v.v[i]; }
+};
+template <>
+struct RawActions<uint8_t, 4> {
+  uint32_t w;
+  __device__ __forceinline__ void load(const uint8_t* p) { w = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ void zero() { w = 0; }
+  __device__ __forceinline__ uint8_t get(int i) const { return (uint8_t)(w >> (8 * i)); }
+};
+
 // ---- per-thread episode statistics, reduced once per CTA ---------------------------------
 struct StatAcc {
   uint32_t episodes = 0, terminated = 0, truncated = 0;
@@ -723,32 +743,33 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
       }
     }
 
-    Vec<act_t, V> a_next;
-#pragma unroll
-    for (int v = 0; v < V; ++v) a_next.v[v] = act_t(0);
-    if (!policy && active) a_next = ldv<act_t, V>(actions + base);
+    RawActions<act_t, V> a_next;
+    a_next.zero();
+    if (!policy && active) a_next.load(actions + base);
 
     for (uint32_t kk = 0; kk < p.K; ++kk) {
       const uint64_t t = p.t + kk;
+      const RawActions<act_t, V> a_cur = a_next;
+      // prefetch the next step's actions first: the load stays in flight for the whole step
+      if (!policy && active && kk + 1 < p.K) a_next.load(actions + (uint64_t)(kk + 1) * p.n + base);
       act_t action[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) action[v] = a_next.v[v];
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
         if constexpr (V == 4) {
-          const uint4 w = philox_env(p.keys, (p.env_base + base) >> 2, t, TAG_ACTION);
+          const uint4 w = philox_env(p.seed, (p.env_base + base) >> 2, t, TAG_ACTION);
           action[0] = action_from_word<KIND>(w.x);
           action[1] = action_from_word<KIND>(w.y);
           action[2] = action_from_word<KIND>(w.z);
           action[3] = action_from_word<KIND>(w.w);
         } else {
           const uint64_t gid = p.env_base + base;
-          const uint4 w = philox_env(p.keys, gid >> 2, t, TAG_ACTION);
+          const uint4 w = philox_env(p.seed, gid >> 2, t, TAG_ACTION);
           const uint32_t lane_word = (gid & 2) ? ((gid & 1) ? w.w : w.z) : ((gid & 1) ? w.y : w.x);
           action[0] = action_from_word<KIND>(lane_word);
         }
-      } else if (active && kk + 1 < p.K) {
-        a_next = ldv<act_t, V>(actions + (uint64_t)(kk + 1) * p.n + base);  // prefetch next step
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) action[v] = a_cur.get(v);
       }
       if constexpr (!E::CONTINUOUS) {
         if (p.bad_action) {
