@@ -140,7 +140,7 @@ int mgym_reset_masked(mgym_env *env, const uint8_t *mask, float *obs_out, void *
 int mgym_set_reset_pool(mgym_env *env, const float *pool, uint64_t pool_len, void *stream);
 
 /* ---- state injection / checkpoint (Testable::set_state) --------------------------- */
-/* state: SoA [state_dim][N]; steps, sbt: uint32[N] or NULL (-> 0 / None).
+/* state: SoA [state_dim][N]; steps, sbt: uint32[N] or NULL (-> 0 / None); device or host pointers.
  * sbt encodes steps_beyond_terminated: 0 = None, k+1 = Some(k). */
 int mgym_set_state(mgym_env *env, const float *state, const uint32_t *steps, const uint32_t *sbt, void *stream);
 int mgym_get_state(mgym_env *env, float *state, uint32_t *steps, uint32_t *sbt, void *stream);

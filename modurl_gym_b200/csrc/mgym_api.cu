@@ -295,6 +295,15 @@ int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* m
   return MGYM_OK;
 }
 
+bool is_host_pointer(const void* ptr) {
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost;
+}
+
 int check_bad_action(mgym_env* e, cudaStream_t st) {
   if (!e->cfg.validate_actions) return MGYM_OK;
   uint32_t bad = 0;
@@ -549,8 +558,19 @@ int mgym_set_state(mgym_env* e, const float* state, const uint32_t* steps, const
     else MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint32_t) * n, st));
   } else if (e->cnt_mode == CNT_U16) {
     if (steps) {
-      convert_kernel<uint32_t, uint16_t><<<blocks, 256, 0, st>>>(steps, (uint16_t*)e->steps, n);
+      const uint32_t* src = steps;
+      uint32_t* tmp = nullptr;
+      if (is_host_pointer(steps)) {  // set_state/get_state also accept host arrays
+        MGYM_CUDA(cudaMalloc(&tmp, sizeof(uint32_t) * n));
+        MGYM_CUDA(cudaMemcpyAsync(tmp, steps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        src = tmp;
+      }
+      convert_kernel<uint32_t, uint16_t><<<blocks, 256, 0, st>>>(src, (uint16_t*)e->steps, n);
       MGYM_CUDA(cudaGetLastError());
+      if (tmp) {
+        MGYM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+      }
     } else {
       MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint16_t) * n, st));
     }
@@ -574,14 +594,27 @@ int mgym_get_state(mgym_env* e, float* state, uint32_t* steps, uint32_t* sbt, vo
     if (e->cnt_mode == CNT_U32) {
       MGYM_CUDA(cudaMemcpyAsync(steps, e->steps, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
     } else if (e->cnt_mode == CNT_U16) {
-      convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, steps, n);
-      MGYM_CUDA(cudaGetLastError());
+      if (is_host_pointer(steps)) {
+        uint32_t* tmp = nullptr;
+        MGYM_CUDA(cudaMalloc(&tmp, sizeof(uint32_t) * n));
+        convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, tmp, n);
+        MGYM_CUDA(cudaGetLastError());
+        MGYM_CUDA(cudaMemcpyAsync(steps, tmp, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+        MGYM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+      } else {
+        convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, steps, n);
+        MGYM_CUDA(cudaGetLastError());
+      }
+    } else if (is_host_pointer(steps)) {
+      memset(steps, 0, sizeof(uint32_t) * n);
     } else {
       MGYM_CUDA(cudaMemsetAsync(steps, 0, sizeof(uint32_t) * n, st));
     }
   }
   if (sbt) {
     if (e->sbt) MGYM_CUDA(cudaMemcpyAsync(sbt, e->sbt, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
+    else if (is_host_pointer(sbt)) memset(sbt, 0, sizeof(uint32_t) * n);
     else MGYM_CUDA(cudaMemsetAsync(sbt, 0, sizeof(uint32_t) * n, st));
   }
   return MGYM_OK;

@@ -42,3 +42,11 @@ for folder in ("cartpole", "mountain_car"):
     with open(dst, "w") as f:
         json.dump(doc, f, separators=(",", ":"))
     print("wrote", dst, os.path.getsize(dst), "bytes")
+    # the same vectors as flat text for the C++ test: action obs... reward done truncated (floats as %.9g)
+    txt = os.path.join(HERE, f"{folder}_gymnasium.txt")
+    with open(txt, "w") as f:
+        f.write(f"# from python_tests/{folder}/{{inputs,output}}.json; columns: action obs[{len(outputs[0]['observation'])}] reward done truncated\n")
+        for a, o in zip(actions, outputs):
+            cols = [str(a)] + ["%.9g" % x for x in o["observation"]] + ["%.9g" % o["reward"], str(int(o["done"])), str(int(o["truncated"]))]
+            f.write(" ".join(cols) + "\n")
+    print("wrote", txt)
