@@ -938,6 +938,7 @@ __global__ void trig_probe_kernel(const float* x, float* s, float* c, float* s_o
 //   mode 0: fdiv_const_fast(x, c, rc) vs __fdiv_rn(x, c) for every bit pattern x in [first, first+n) with div_safe(x)
 //   mode 1: sincos_small vs sincos_ref for every bit pattern with abstop12 < 0x3f4
 //   mode 2: cos_fast vs cos_ref for every bit pattern with abstop12 < 0x42f
+//   mode 3: fmod_fast(x, 2 pi) vs fmodf for every |x| < 2^22;  mode 4: sincos_fast vs sincos_ref, |x| < 120
 __global__ void fast_exhaustive_kernel(int mode, uint64_t first, uint64_t n, float c, float rc,
                                        unsigned long long* checked, unsigned long long* bad, uint32_t* first_bad) {
   unsigned long long my_checked = 0, my_bad = 0;
@@ -956,9 +957,21 @@ __global__ void fast_exhaustive_kernel(int mode, uint64_t first, uint64_t n, flo
         sincos_ref(x, s1, c1);
         mismatch = __float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1);
       }
-    } else {
+    } else if (mode == 2) {
       applicable = abstop12(x) < 0x42f;
       if (applicable) mismatch = __float_as_uint(cos_fast(x)) != __float_as_uint(cos_ref(x));
+    } else if (mode == 3) {  // fmod_fast(t, 2 pi) vs fmodf, |t| < 2^22
+      applicable = fabsf(x) < 4194304.0f;
+      if (applicable)
+        mismatch = __float_as_uint(fmod_fast(x, TWO_PI_F, 0.15915494309189535f)) != __float_as_uint(fmodf(x, TWO_PI_F));
+    } else {  // sincos_fast vs sincos_ref, |x| < 120
+      applicable = abstop12(x) < 0x42f;
+      if (applicable) {
+        float s0, c0, s1, c1;
+        sincos_fast(x, s0, c0);
+        sincos_ref(x, s1, c1);
+        mismatch = __float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1);
+      }
     }
     my_checked += applicable ? 1 : 0;
     if (mismatch) {

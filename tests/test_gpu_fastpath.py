@@ -3,7 +3,8 @@
 Checked ON THE DEVICE, exhaustively where the domain is one float (all 2^32 bit patterns):
   * fdiv_const_fast(x, total_mass)  ==  __fdiv_rn(x, total_mass)   for every div_safe(x)
   * sincos_small(x)                 ==  sincos_ref(x)              for every |x| < 0.75
-  * cos_fast(x)                     ==  cos_ref(x)                 for every |x| < 120
+  * cos_fast(x), sincos_fast(x)     ==  cos_ref(x), sincos_ref(x)  for every |x| < 120
+  * fmod_fast(x, 2 pi)              ==  fmodf(x, 2 pi)             for every |x| < 2^22
 and on 2^29 Philox-drawn pairs for the two-operand fdiv_fast(a, b) == __fdiv_rn(a, b).
 sincos_ref / cos_ref themselves are pinned to the oracle (and so to glibc) in test_gpu_parity.py."""
 import ctypes as C
@@ -29,6 +30,8 @@ def lib():
     (0, "fdiv_const_fast", 2 * 120 * (1 << 23)),
     (1, "sincos_small", 2 * 0x3f400000 - 10),
     (2, "cos_fast", 2 * 0x42f00000 - 10),
+    (3, "fmod_fast", 2 * 0x4a800000 - 10),
+    (4, "sincos_fast", 2 * 0x42f00000 - 10),
 ])
 def test_fast_form_exhaustive(lib, mode, name, min_checked):
     out = (C.c_uint64 * 3)()
