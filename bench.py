@@ -67,7 +67,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -104,6 +104,16 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[f"{KIND_NAME}/{n}/step"]
+        return t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+    except Exception:
+        return None, None
 
 
 def measured_peak_gbs():
@@ -249,6 +259,7 @@ def run_native(args, rank, local_rank, world):
         launch_s = ms_max * 1e-3 / args.steps
         peak, peak_src = measured_peak_gbs()
         achieved = BYTES_PER_ENV_STEP * n / launch_s / 1e9
+        traffic, traffic_src = ncu_traffic(n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -261,7 +272,8 @@ def run_native(args, rank, local_rank, world):
                 "parallelism": f"dp{world} (independent env slices, no data-path collective)",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "step_kernel_tma<CartPole-v1, u16 counter>",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n, "kernel": "step_kernel_tma<CartPole-v1, u16 counter>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
             "e2e": {"value": float(n) * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
