@@ -149,6 +149,13 @@ int mgym_get_obs(mgym_env *env, float *obs_out, void *stream);
  * state (CartPole, MountainCar, MountainCarContinuous) this IS the observation buffer. */
 float *mgym_state_ptr(mgym_env *env);
 
+/* Checkpoint / resume: the whole handle (state rows, counters, running returns, statistics, step and reset
+ * indices) as one opaque HOST blob.  mgym_checkpoint_size gives the byte count; a handle created with the same
+ * kind, num_envs and config continues bit-identically after mgym_checkpoint_load. */
+size_t mgym_checkpoint_size(const mgym_env *env);
+int mgym_checkpoint_save(mgym_env *env, void *host_blob, size_t blob_bytes, void *stream);
+int mgym_checkpoint_load(mgym_env *env, const void *host_blob, size_t blob_bytes, void *stream);
+
 /* ---- the hot path ------------------------------------------------------------------ */
 /* One Gym::step for all N envs.  obs_out, reward_out, flags_out, final_obs_out may be NULL. */
 int mgym_step(mgym_env *env, const void *actions, float *obs_out, float *reward_out, uint8_t *flags_out,
@@ -173,7 +180,8 @@ int mgym_stats_reset(mgym_env *env, void *stream);
  * DEVICE buffer: this is the vector a host layer all-reduces (sum) across GPUs. */
 int mgym_stats_export(mgym_env *env, double *device_vec5_out, void *stream);
 /* mgym_stats_export followed by ncclAllReduce(sum) in place on `comm` (an ncclComm_t).  NCCL is
- * resolved at run time from the process (dlsym), so the library carries no NCCL link dependency. */
+ * resolved at run time from the process (dlsym), so the library carries no NCCL link dependency.  A single
+ * thread that drives several GPUs brackets the calls with ncclGroupStart/ncclGroupEnd as usual. */
 int mgym_stats_allreduce(mgym_env *env, void *nccl_comm, double *device_vec5_out, void *stream);
 
 #ifdef __cplusplus

@@ -72,6 +72,9 @@ SYMBOLS = {
     "mgym_get_state": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "mgym_get_obs": (_i, [_vp, _vp, _vp]),
     "mgym_state_ptr": (_vp, [_vp]),
+    "mgym_checkpoint_size": (C.c_size_t, [_vp]),
+    "mgym_checkpoint_save": (_i, [_vp, _vp, C.c_size_t, _vp]),
+    "mgym_checkpoint_load": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "mgym_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mgym_rollout": (_i, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mgym_sample_actions": (_i, [_vp, _vp, _vp]),

@@ -637,6 +637,88 @@ int mgym_get_obs(mgym_env* e, float* obs_out, void* stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// checkpoint / resume
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct CheckpointHeader {
+  uint32_t magic, version;
+  int32_t kind, cnt_mode, auto_reset, has_sbt, has_ret;
+  uint64_t n, seed, t, n_resets;
+};
+constexpr uint32_t kCkptMagic = 0x4D47594Du;  // "MGYM"
+
+size_t counter_bytes(const mgym_env* e) {
+  return e->cnt_mode == CNT_NONE ? 0 : (e->cnt_mode == CNT_U16 ? 2 : 4) * (size_t)e->n;
+}
+}  // namespace
+
+size_t mgym_checkpoint_size(const mgym_env* e) {
+  if (!e) return 0;
+  const size_t n = (size_t)e->n;
+  return sizeof(CheckpointHeader) + sizeof(float) * kStateDim[e->kind] * n + counter_bytes(e) +
+         (e->sbt ? sizeof(uint32_t) * n : 0) + (e->ep_return ? sizeof(float) * n : 0) + 5 * sizeof(unsigned long long);
+}
+
+int mgym_checkpoint_save(mgym_env* e, void* blob, size_t blob_bytes, void* stream) {
+  if (!e || !blob) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_save: NULL argument");
+  if (blob_bytes < mgym_checkpoint_size(e)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_save: blob too small");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  CheckpointHeader h{kCkptMagic, 1, e->kind, e->cnt_mode, e->cfg.auto_reset, e->sbt ? 1 : 0, e->ep_return ? 1 : 0,
+                     e->n,      e->seed, e->t, e->n_resets};
+  uint8_t* out = static_cast<uint8_t*>(blob);
+  memcpy(out, &h, sizeof(h));
+  out += sizeof(h);
+  auto pull = [&](const void* dev, size_t bytes) -> int {
+    if (bytes) MGYM_CUDA(cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, st));
+    out += bytes;
+    return MGYM_OK;
+  };
+  int rc;
+  if ((rc = pull(e->state, sizeof(float) * kStateDim[e->kind] * n))) return rc;
+  if ((rc = pull(e->steps, counter_bytes(e)))) return rc;
+  if ((rc = pull(e->sbt, e->sbt ? sizeof(uint32_t) * n : 0))) return rc;
+  if ((rc = pull(e->ep_return, e->ep_return ? sizeof(float) * n : 0))) return rc;
+  if ((rc = pull(e->stats, 5 * sizeof(unsigned long long)))) return rc;
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  return MGYM_OK;
+}
+
+int mgym_checkpoint_load(mgym_env* e, const void* blob, size_t blob_bytes, void* stream) {
+  if (!e || !blob) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: NULL argument");
+  if (blob_bytes < sizeof(CheckpointHeader)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: truncated blob");
+  CheckpointHeader h;
+  memcpy(&h, blob, sizeof(h));
+  if (h.magic != kCkptMagic || h.version != 1) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: not a checkpoint");
+  if (h.kind != e->kind || h.n != e->n || h.cnt_mode != e->cnt_mode || h.auto_reset != e->cfg.auto_reset ||
+      h.has_sbt != (e->sbt ? 1 : 0) || h.has_ret != (e->ep_return ? 1 : 0))
+    return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: checkpoint of %s x %llu does not match this handle",
+                valid_kind(h.kind) ? kNames[h.kind] : "?", (unsigned long long)h.n);
+  if (blob_bytes < mgym_checkpoint_size(e)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: truncated blob");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  const uint8_t* in = static_cast<const uint8_t*>(blob) + sizeof(h);
+  auto push = [&](void* dev, size_t bytes) -> int {
+    if (bytes) MGYM_CUDA(cudaMemcpyAsync(dev, in, bytes, cudaMemcpyHostToDevice, st));
+    in += bytes;
+    return MGYM_OK;
+  };
+  int rc;
+  if ((rc = push(e->state, sizeof(float) * kStateDim[e->kind] * n))) return rc;
+  if ((rc = push(e->steps, counter_bytes(e)))) return rc;
+  if ((rc = push(e->sbt, e->sbt ? sizeof(uint32_t) * n : 0))) return rc;
+  if ((rc = push(e->ep_return, e->ep_return ? sizeof(float) * n : 0))) return rc;
+  if ((rc = push(e->stats, 5 * sizeof(unsigned long long)))) return rc;
+  MGYM_CUDA(cudaStreamSynchronize(st));
+  e->seed = h.seed;
+  e->t = h.t;
+  e->n_resets = h.n_resets;
+  return MGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // hot path
 // ---------------------------------------------------------------------------------------------
 int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_out, uint8_t* flags_out,

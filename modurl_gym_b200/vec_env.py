@@ -192,6 +192,18 @@ class GpuVecEnv:
         _lib.check(self._lib.mgym_get_obs(self._h, _ptr(obs), self._stream()))
         return obs
 
+    def checkpoint(self):
+        """The whole handle (state, counters, running returns, statistics, step/reset indices) as bytes."""
+        size = self._lib.mgym_checkpoint_size(self._h)
+        buf = (C.c_uint8 * size)()
+        _lib.check(self._lib.mgym_checkpoint_save(self._h, buf, size, self._stream()))
+        return bytes(buf)
+
+    def restore(self, blob):
+        """Resume from `checkpoint()` of a handle with the same kind, size and config: continues bit-identically."""
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _lib.check(self._lib.mgym_checkpoint_load(self._h, buf, len(blob), self._stream()))
+
     def set_reset_pool(self, pool):
         """Injected reset states [state_dim, P] (parity runs); None restores Philox."""
         if pool is None:

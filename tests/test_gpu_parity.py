@@ -485,3 +485,23 @@ def test_step_host_round_trip(gym, oracle):
         assert_bit_equal(obs.numpy(), o, "obs")
         assert_bit_equal(flg.numpy(), f, "flags")
         assert_bit_equal(rew.numpy(), r, "reward")
+
+
+@pytest.mark.parametrize("kind", range(5))
+def test_checkpoint_resume_is_bit_identical(gym, kind):
+    """SURVEY 5 (checkpoint / resume): save after K steps, restore into a fresh handle, continue: same bits as the
+    uninterrupted run, including the Philox stream position and the statistics."""
+    n, K = 4096, {0: 120, 1: 120, 2: 120, 3: 230, 4: 40}[kind]
+    a = gym.GpuVecEnv(kind, n, seed=31)
+    a.reset()
+    a.rollout(K)
+    blob = a.checkpoint()
+    want = a.rollout(K)
+    b = gym.GpuVecEnv(kind, n, seed=999)      # different seed on purpose: the checkpoint carries it
+    b.restore(blob)
+    got = b.rollout(K)
+    assert torch.equal(got.obs.view(torch.int32), want.obs.view(torch.int32))
+    assert torch.equal(got.flags, want.flags) and torch.equal(got.reward.view(torch.int32), want.reward.view(torch.int32))
+    assert a.stats() == b.stats() and a.step_index == b.step_index
+    with pytest.raises(gym.MgymError):
+        gym.GpuVecEnv(kind, n // 2).restore(blob)
