@@ -212,12 +212,29 @@ int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, L::SMEM_BYTES));
   if (per_sm < 1) per_sm = 1;
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
-  uint64_t blocks = (uint64_t)e->num_sms * per_sm;
-  const uint64_t need = p.n / TMA_TILE;
-  if (blocks > need) blocks = need;
+  // Static round-robin tiles: every CTA runs ceil(tiles / grid) rounds, so use the SMALLEST grid that
+  // still needs the same number of rounds as the full machine -- the last round is then nearly full
+  // (2^24 envs: 16384 tiles, 296 slots -> 56 rounds -> 293 CTAs, 99.9 % balanced instead of 98.8 %).
+  const uint64_t slots = (uint64_t)e->num_sms * per_sm;
+  const uint64_t tiles = p.n / TMA_TILE;
+  const uint64_t rounds = (tiles + slots - 1) / slots;
+  uint64_t blocks = (tiles + rounds - 1) / rounds;
   if (blocks < 1) blocks = 1;
-  kernel<<<(unsigned)blocks, threads, L::SMEM_BYTES, st>>>(p);
-  MGYM_CUDA(cudaGetLastError());
+  static const bool pdl = [] {
+    const char* s = getenv("MGYM_NO_PDL");
+    return !(s && atoi(s) != 0);
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = L::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MGYM_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
   return MGYM_OK;
 }
 

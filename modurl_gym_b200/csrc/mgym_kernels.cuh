@@ -550,6 +550,11 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     tma::fence_mbar_init();
   }
   __syncthreads();
+  // Programmatic dependent launch: everything above overlaps the tail of the previous launch on this
+  // stream (usually the previous step); nothing below may run before that launch has completed and
+  // flushed.  Our own dependents may start their prologue as soon as they find room.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
 
   if (warp == TMA_CONSUMER_WARPS) {
     // ---------------- producer ----------------
