@@ -160,13 +160,6 @@ KernelParams base_params(const mgym_env* e) {
   p.bad_action = e->cfg.validate_actions ? e->bad_action : nullptr;
   p.n = e->n;
   p.seed = e->seed;
-  {
-    uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
-    for (int r = 0; r < 10; ++r) {
-      p.keys.k[r][0] = k0, p.keys.k[r][1] = k1;
-      k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
-    }
-  }
   p.env_base = e->cfg.env_index_base;
   p.t = e->t;
   p.k = e->k;

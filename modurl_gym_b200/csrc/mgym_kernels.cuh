@@ -15,20 +15,8 @@
 #ifndef MGYM_MIN_BLOCKS
 #define MGYM_MIN_BLOCKS 1
 #endif
-#ifndef MGYM_EXP_STCS
-#define MGYM_EXP_STCS 0
-#endif
-#ifndef MGYM_EXP_LDHINT
-#define MGYM_EXP_LDHINT 0
-#endif
 #ifndef MGYM_EXP_MEMONLY
 #define MGYM_EXP_MEMONLY 0
-#endif
-#ifndef MGYM_EXP_KEYS
-#define MGYM_EXP_KEYS 0
-#endif
-#ifndef MGYM_EXP_STATS
-#define MGYM_EXP_STATS 1
 #endif
 #ifndef MGYM_ROLLOUT_MIN_BLOCKS
 #define MGYM_ROLLOUT_MIN_BLOCKS 2
@@ -61,7 +49,6 @@ struct KernelParams {
   unsigned long long* done_count;  // rollout: finished env-steps
   uint32_t* bad_action;            // validate_actions: set to 1 on an out-of-range discrete action
   uint64_t n, seed, env_base, t;
-  PhiloxKeys keys;  // round keys of `seed`
   uint32_t K;
   EnvConsts k;
 };
@@ -96,24 +83,12 @@ __device__ __forceinline__ void stv(T* p, const Vec<T, V>& r) {
   if constexpr (V == 1) {
     *p = r.v[0];
   } else if constexpr (sizeof(T) * V == 16) {
-#if MGYM_EXP_STCS
-    __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&r));
-#else
     *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&r);
-#endif
   } else if constexpr (sizeof(T) * V == 8) {
-#if MGYM_EXP_STCS
-    __stcs(reinterpret_cast<uint2*>(p), *reinterpret_cast<const uint2*>(&r));
-#else
     *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(&r);
-#endif
   } else {
     static_assert(sizeof(T) * V == 4, "unsupported vector width");
-#if MGYM_EXP_STCS
-    __stcs(reinterpret_cast<unsigned int*>(p), *reinterpret_cast<const unsigned int*>(&r));
-#else
     *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&r);
-#endif
   }
 }
 
@@ -266,7 +241,6 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
     if constexpr (AUTO) {
       const bool done = g.flags[v] != 0;
       pending |= done ? (1u << v) : 0u;
-#if MGYM_EXP_STATS
       // flags are 0 for a live env, so the masks need no extra select
       const uint32_t fl = count ? g.flags[v] : 0u;
       acc.episodes += fl != 0 ? 1u : 0u;
@@ -274,13 +248,6 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
       acc.truncated += fl >> 1;
       acc.length_sum += fl != 0 ? g.steps[v] : 0u;
       const bool tally = fl != 0;
-#else
-      const bool tally = count && done;
-      acc.episodes += tally ? 1u : 0u;
-      acc.terminated += tally ? (g.flags[v] & FLAG_TERMINATED) : 0u;
-      acc.truncated += tally ? ((g.flags[v] & FLAG_TRUNCATED) >> 1) : 0u;
-      acc.length_sum += tally ? g.steps[v] : 0u;
-#endif
       if constexpr (!E::ANALYTIC_RETURN) {
         if (tally) acc.return_sum += (double)g.ret[v];
       }
@@ -297,11 +264,7 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
 #pragma unroll
         for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
       } else {
-        #if MGYM_EXP_KEYS
-        E::reset(philox_env(p.keys, gid, t, TAG_AUTO_RESET), ns);
-#else
-        E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
-#endif
+                E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
       }
       if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
 #pragma unroll
@@ -459,24 +422,10 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
-#if MGYM_EXP_LDHINT
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          dst),
-      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-      : "memory");
-#else
-  (void)pol;
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -561,7 +510,6 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     if (lane == 0) {
       const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
       const uint32_t tx = SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u);
-      const uint64_t pol = tma::policy_evict_first();
       uint32_t it = 0;
       for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
@@ -570,12 +518,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         const uint64_t e0 = tile * TMA_TILE;
         tma::mbar_expect_tx(bar, tx);
 #pragma unroll
-        for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar, pol);
-        tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar, pol);
+        for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar);
+        tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
         if constexpr (CNT != CNT_NONE)
-          tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar, pol);
+          tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
         if constexpr (!E::ANALYTIC_RETURN) {
-          if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar, pol);
+          if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
         }
       }
     }
