@@ -457,10 +457,14 @@ static inline void acrobot_dsdt(const acrobot_params *p, const float s[4], float
   d[3] = ddtheta2;
 }
 
+/* Gymnasium's wrap() loops `while x > M: x -= diff` without bound, which never ends for a huge or infinite
+ * x (x - 2*pi == x).  From any state the step itself can produce, |x| < 4*pi and at most two passes run, so
+ * the loops are capped at 4 passes: same values on every reachable state, and termination on garbage. */
+#define ORACLE_WRAP_MAX_PASSES 4
 static inline float wrapf(float x, float m, float M) {
   float diff = M - m;
-  while (x > M) x = x - diff;
-  while (x < m) x = x + diff;
+  for (int i = 0; i < ORACLE_WRAP_MAX_PASSES && x > M; ++i) x = x - diff;
+  for (int i = 0; i < ORACLE_WRAP_MAX_PASSES && x < m; ++i) x = x + diff;
   return x;
 }
 

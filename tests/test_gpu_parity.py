@@ -505,3 +505,55 @@ def test_checkpoint_resume_is_bit_identical(gym, kind):
     assert a.stats() == b.stats() and a.step_index == b.step_index
     with pytest.raises(gym.MgymError):
         gym.GpuVecEnv(kind, n // 2).restore(blob)
+
+
+# ---------------------------------------------------------------------------------------------
+# states outside every fast-path precondition: the reference-form fallback must give the oracle's bits
+# ---------------------------------------------------------------------------------------------
+def assert_equal_or_both_nan(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    both_nan = np.isnan(got) & np.isnan(want)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | both_nan
+    if not same.all():
+        idx = tuple(np.argwhere(~same)[0])
+        raise AssertionError(f"{what}: {int((~same).sum())} differ; first at {idx}: got {got[idx]!r} want {want[idx]!r}")
+
+
+def adversarial_states(kind, n, rng):
+    sd = STATE_DIM[kind]
+    big = np.array([0.0, -0.0, 1e-45, 1e-30, 0.7499, 0.75, 0.7501, 0.7853982, 1.5, 3.1415927, 10.0, 119.9, 120.0, 121.0,
+                    1e4, 4194304.0, 1e7, 1e10, 1e20, 3e38, np.inf, np.nan], dtype=np.float32)
+    s = np.zeros((sd, n), dtype=np.float32)
+    for c in range(sd):
+        s[c] = rng.choice(big, size=n) * rng.choice(np.array([-1.0, 1.0], dtype=np.float32), size=n)
+    # keep a fraction ordinary so that fast and fallback envs share warps and threads
+    ordinary = rng.random(n) < 0.5
+    s[:, ordinary] = random_states(rng, kind, int(ordinary.sum()))
+    return s
+
+
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("auto", [True, False])
+def test_fallback_paths_match_oracle(gym, oracle, kind, auto):
+    n = 4096
+    rng = np.random.default_rng(900 + kind)
+    env = gym.GpuVecEnv(kind, n, auto_reset=auto, seed=4)
+    ref = oracle.VecState(kind, n, auto_reset=int(auto), seed=4)
+    env.reset(), ref.reset()
+    with np.errstate(all="ignore"):
+        for rep in range(3):
+            st = adversarial_states(kind, n, rng)
+            env.set_state(dev(st))
+            ref.state[:] = st
+            ref.steps[:] = 0
+            ref.sbt[:] = 0
+            ref.ep_return[:] = 0
+            for t in range(3):
+                a = random_actions(rng, kind, n)
+                info = env.step(dev(a))
+                o, r, f = ref.step(a)
+                flags = host(info.done).astype(np.uint8) | (host(info.truncated).astype(np.uint8) << 1)
+                assert_bit_equal(flags, f, f"{KIND_NAMES[kind]} flags rep {rep} t {t}")
+                assert_equal_or_both_nan(host(info.state), o, f"{KIND_NAMES[kind]} obs rep {rep} t {t}")
+                assert_equal_or_both_nan(host(info.reward), r, f"{KIND_NAMES[kind]} reward rep {rep} t {t}")
+    env.close()
