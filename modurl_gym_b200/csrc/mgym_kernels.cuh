@@ -197,7 +197,7 @@ struct Group {
   uint32_t flags[V];
 };
 
-template <int KIND, int V, bool AUTO, bool WANT_FINAL>
+template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true>
 __device__ __forceinline__ void step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
                                            const typename Env<KIND>::act_t (&action)[V], bool track_ret,
                                            Group<KIND, V>& g, StatAcc& acc) {
@@ -246,7 +246,7 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
       acc.episodes += fl != 0 ? 1u : 0u;
       acc.terminated += fl & FLAG_TERMINATED;
       acc.truncated += fl >> 1;
-      acc.length_sum += fl != 0 ? g.steps[v] : 0u;
+      if constexpr (TALLY_LEN) acc.length_sum += fl != 0 ? g.steps[v] : 0u;
       const bool tally = fl != 0;
       if constexpr (!E::ANALYTIC_RETURN) {
         if (tally) acc.return_sum += (double)g.ret[v];
@@ -700,11 +700,30 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
     a_next.zero();
     if (!policy && active) a_next.load(actions + base);
 
+    // Sum of the lengths of the episodes an env finishes during this launch = steps_before + K - steps_after,
+    // so the per-step tally is not needed here (counters saturate only after 4e9 steps).
+    constexpr bool kLenIdentity = AUTO && CNT != CNT_NONE;
+    uint32_t steps_before = 0;
+    if constexpr (kLenIdentity) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) steps_before += g.steps[v];
+    }
+
+    // running output pointers: one 64-bit add per array per step instead of a multiply-add chain per store
+    const uint64_t obs_step = (uint64_t)OD * p.n;
+    float* obs_ptr = p.obs_out ? p.obs_out + base : nullptr;
+    float* rew_ptr = p.reward_out ? p.reward_out + base : nullptr;
+    uint8_t* flg_ptr = p.flags_out ? p.flags_out + base : nullptr;
+    const act_t* act_ptr = actions ? actions + base + p.n : nullptr;  // next step's row
+
     for (uint32_t kk = 0; kk < p.K; ++kk) {
       const uint64_t t = p.t + kk;
       const RawActions<act_t, V> a_cur = a_next;
       // prefetch the next step's actions first: the load stays in flight for the whole step
-      if (!policy && active && kk + 1 < p.K) a_next.load(actions + (uint64_t)(kk + 1) * p.n + base);
+      if (!policy && active && kk + 1 < p.K) {
+        a_next.load(act_ptr);
+        act_ptr += p.n;
+      }
       act_t action[V];
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
@@ -732,33 +751,43 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
         }
       }
 
-      step_group<KIND, V, AUTO, false>(p, active, base, t, action, track_ret, g, acc);
+      step_group<KIND, V, AUTO, false, !kLenIdentity>(p, active, base, t, action, track_ret, g, acc);
 
 #pragma unroll
       for (int v = 0; v < V; ++v) warp_dones += __popc(__ballot_sync(0xffffffffu, active && g.flags[v] != 0));
       if (active) {
-        if (p.obs_out) {
-          float* ob = p.obs_out + (uint64_t)kk * OD * p.n + base;
+        if (obs_ptr) {
 #pragma unroll
           for (int c = 0; c < OD; ++c) {
             Vec<float, V> o;
 #pragma unroll
             for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-            stv<float, V>(ob + (uint64_t)c * p.n, o);
+            stv<float, V>(obs_ptr + (uint64_t)c * p.n, o);
           }
+          obs_ptr += obs_step;
         }
-        if (p.reward_out) {
+        if (rew_ptr) {
           Vec<float, V> rw;
 #pragma unroll
           for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
-          stv<float, V>(p.reward_out + (uint64_t)kk * p.n + base, rw);
+          stv<float, V>(rew_ptr, rw);
+          rew_ptr += p.n;
         }
-        if (p.flags_out) {
+        if (flg_ptr) {
           Vec<uint8_t, V> fl;
 #pragma unroll
           for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
-          stv<uint8_t, V>(p.flags_out + (uint64_t)kk * p.n + base, fl);
+          stv<uint8_t, V>(flg_ptr, fl);
+          flg_ptr += p.n;
         }
+      }
+    }
+    if constexpr (kLenIdentity) {
+      if (active) {
+        uint32_t steps_after = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) steps_after += g.steps[v];
+        acc.length_sum += (unsigned long long)steps_before + (unsigned long long)V * p.K - steps_after;
       }
     }
 
