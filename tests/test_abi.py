@@ -105,3 +105,10 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "mgym_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_rust_sys_declares_every_entry_point():
+    """bindings/rust/src/sys.rs (uncompiled skeleton) must at least name every function of include/mgym.h."""
+    text = open(os.path.join(ROOT, "bindings", "rust", "src", "sys.rs")).read()
+    declared = set(re.findall(r"pub fn (mgym_[a-z_0-9]+)\(", text))
+    assert declared == set(declared_symbols())
