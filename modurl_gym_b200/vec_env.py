@@ -158,6 +158,24 @@ class GpuVecEnv:
                                           self._stream()))
         return Rollout(obs, reward, flags, dc)
 
+    def iter_rollout(self, total_steps, chunk=32, actions=None, want_obs=True):
+        """A long rollout (e.g. MountainCar's 1000 steps, BASELINE configs[2]) as fused launches of `chunk` steps
+        over ONE reused trajectory ring: the full trajectory of 2^24 envs x 1000 steps would be 218 GB.
+        Yields (first_step, Rollout) per launch; the Rollout tensors are overwritten by the next launch.
+        actions: None (device policy) or a callable first_step, n_steps -> [n_steps, N] tensor."""
+        n, K = self.num_envs, int(chunk)
+        obs = torch.empty((K, self.obs_dim, n), dtype=torch.float32, device=self.device) if want_obs else None
+        reward = torch.empty((K, n), dtype=torch.float32, device=self.device)
+        flags = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        done = 0
+        while done < total_steps:
+            k = min(K, total_steps - done)
+            a = None if actions is None else actions(done, k)
+            out = self.rollout(k, a, obs=None if obs is None else obs[:k], reward=reward[:k], flags=flags[:k],
+                               want_obs=want_obs)
+            yield done, out
+            done += k
+
     def sample_actions(self, out=None):
         """action_space().sample(device) for every env (cartpole.rs:461)."""
         if out is None:

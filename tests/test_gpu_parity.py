@@ -557,3 +557,23 @@ def test_fallback_paths_match_oracle(gym, oracle, kind, auto):
                 assert_equal_or_both_nan(host(info.state), o, f"{KIND_NAMES[kind]} obs rep {rep} t {t}")
                 assert_equal_or_both_nan(host(info.reward), r, f"{KIND_NAMES[kind]} reward rep {rep} t {t}")
     env.close()
+
+
+def test_mountain_car_1000_step_chunked_rollout(gym, oracle):
+    """BASELINE configs[2]: a 1000-step MountainCar rollout run as 32-step launches over one reused ring equals
+    the oracle's single 1000-step rollout (flags, rewards, observations of every step, final state)."""
+    n, T = 512, 1000
+    env = gym.GpuVecEnv(1, n, seed=8)
+    ref = oracle.VecState(1, n, auto_reset=1, seed=8)
+    env.reset(), ref.reset()
+    o, r, f, dones = ref.rollout(T)
+    total_done = 0
+    for first, out in env.iter_rollout(T, chunk=32):
+        k = out.flags.shape[0]
+        assert_bit_equal(host(out.obs), o[first:first + k], f"obs of steps [{first},{first + k})")
+        assert_bit_equal(host(out.flags), f[first:first + k], "flags")
+        assert_bit_equal(host(out.reward), r[first:first + k], "reward")
+        total_done += int(out.done_count.item())
+    assert total_done == dones and env.step_index == T
+    state, steps, _ = env.get_state()
+    assert_bit_equal(host(state), ref.state, "final state")
