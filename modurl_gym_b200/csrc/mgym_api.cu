@@ -174,12 +174,19 @@ int env_blocks_per_sm() {
   return v;
 }
 
+// Occupancy of a kernel is a per-device constant: query it once per (kernel instantiation, device).
+constexpr int kMaxDevices = 64;
+
 template <typename Kernel>
 int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, uint64_t groups, cudaStream_t st) {
   constexpr int threads = 256;
-  int per_sm = 0;
-  MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-  if (per_sm < 1) per_sm = 1;
+  static int cached_per_sm[kMaxDevices] = {};  // one table per instantiation; benign if two threads race
+  int per_sm = e->device < kMaxDevices ? cached_per_sm[e->device] : 0;
+  if (per_sm == 0) {
+    MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (e->device < kMaxDevices) cached_per_sm[e->device] = per_sm;
+  }
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
   uint64_t blocks = (uint64_t)e->num_sms * per_sm;
   const uint64_t need = (groups + threads - 1) / threads;
@@ -196,14 +203,15 @@ int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   using L = TmaLayout<KIND, CNT>;
   auto kernel = step_kernel_tma<KIND, CNT>;
   constexpr int threads = TMA_THREADS;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory and the occupancy are per device
+  static int cached_per_sm[kMaxDevices] = {};
+  int per_sm = e->device < kMaxDevices ? cached_per_sm[e->device] : 0;
+  if (per_sm == 0) {
     MGYM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
-    configured = true;
+    MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, L::SMEM_BYTES));
+    if (per_sm < 1) per_sm = 1;
+    if (e->device < kMaxDevices) cached_per_sm[e->device] = per_sm;
   }
-  int per_sm = 0;
-  MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, L::SMEM_BYTES));
-  if (per_sm < 1) per_sm = 1;
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
   // Static round-robin tiles: every CTA runs ceil(tiles / grid) rounds, so use the SMALLEST grid that
   // still needs the same number of rounds as the full machine -- the last round is then nearly full

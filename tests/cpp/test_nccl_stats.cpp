@@ -44,7 +44,14 @@ int main() {
     cfg.env_index_base = d * half;
     CK(mgym_create(MGYM_CARTPOLE_V1, half, d, seed, &cfg, &part[d]));
     CK(mgym_reset(part[d], nullptr, st[d]));
-    CK(mgym_rollout(part[d], K, nullptr, nullptr, nullptr, nullptr, nullptr, st[d]));  // device policy
+    CK(mgym_rollout(part[d], K / 2, nullptr, nullptr, nullptr, nullptr, nullptr, st[d]));  // device policy
+    // per-call steps (the TMA-staged kernel, configured per device) with the same sampled actions
+    unsigned char* acts = nullptr;
+    cudaMalloc(reinterpret_cast<void**>(&acts), half);
+    for (uint32_t k = 0; k < K / 2; ++k) {
+      CK(mgym_sample_actions(part[d], acts, st[d]));
+      CK(mgym_step(part[d], acts, nullptr, nullptr, nullptr, nullptr, st[d]));
+    }
     cudaMalloc(reinterpret_cast<void**>(&vec[d]), 5 * sizeof(double));
   }
   ncclGroupStart();
