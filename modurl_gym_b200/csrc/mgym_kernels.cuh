@@ -205,7 +205,13 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
   float aux[V];
   bool ok[V];
   bool all_ok = true;
-  if constexpr (E::HAS_PAIR && V % 2 == 0) {
+  if constexpr (E::HAS_BATCH) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) aux[v] = 0.0f;
+    E::template dynamics_fast_batch<V>(g.st, action, p.k, ok);
+#pragma unroll
+    for (int v = 0; v < V; ++v) all_ok = all_ok && ok[v];
+  } else if constexpr (E::HAS_PAIR && V % 2 == 0) {
 #pragma unroll
     for (int v = 0; v < V; v += 2) {
       aux[v] = aux[v + 1] = 0.0f;
