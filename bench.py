@@ -116,6 +116,25 @@ def ncu_traffic(n):
         return None, None
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host buffers of the
+    end-to-end leg are allocated on the local NUMA node; matters when 8 ranks stream over PCIe at once."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cpus ({allowed[0]}-{allowed[-1]})"
+    except Exception as e:  # affinity is an optimisation only
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -184,6 +203,7 @@ def run_native(args, rank, local_rank, world):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
     m.load_library()
+    numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
@@ -277,7 +297,8 @@ def run_native(args, rank, local_rank, world):
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
             "e2e": {"value": float(n) * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-                    "path": "mgym_step_host: pinned host actions -> device, step, obs/reward/flags -> pinned host"},
+                    "path": "mgym_step_host: pinned host actions -> device, step, obs/reward/flags -> pinned host",
+                    "host_affinity_rank0": numa},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "episode_stats": {"episodes": stats.episodes, "mean_length": stats.length_sum / max(stats.episodes, 1),
