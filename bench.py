@@ -220,12 +220,11 @@ def run_native(args, rank, local_rank, world):
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
     pool = [torch.randint(0, 2, (n,), dtype=torch.uint8, device=device, generator=gen) for _ in range(16)]
-    reward = torch.empty(n, dtype=torch.float32, device=device)
-    flags = torch.empty(n, dtype=torch.uint8, device=device)
 
     def one_step(i):
-        # obs aliases the resident state rows (zero-copy observation): obs_out = NULL
-        env.step_raw(pool[i & 15], None, reward, flags)
+        # the public call: Gym::step.  For CartPole the returned observation is a view of the resident state rows
+        # (obs_out = NULL in the C call), reward and flags go to the env's own buffers.
+        env.step(pool[i & 15])
 
     def barrier():
         torch.cuda.synchronize()

@@ -25,8 +25,41 @@ KINDS = {
 }
 FLAG_TERMINATED, FLAG_TRUNCATED = 1, 2
 
-# StepInfo { state, reward, done, truncated } (cartpole.rs:300-305), batched.
-StepInfo = namedtuple("StepInfo", ["state", "reward", "done", "truncated"])
+class StepInfo:
+    """StepInfo { state, reward, done, truncated } (cartpole.rs:300-305), batched.
+
+    state [obs_dim, N] f32, reward [N] f32, flags [N] u8 (bit0 = done, bit1 = truncated) are views of buffers the
+    next step overwrites; `done` / `truncated` are boolean tensors derived from `flags` on first use."""
+
+    __slots__ = ("state", "reward", "flags", "_done", "_truncated")
+
+    def __init__(self, state, reward, flags):
+        self.state, self.reward, self.flags = state, reward, flags
+        self._done = self._truncated = None
+
+    @property
+    def done(self):
+        if self._done is None:
+            self._done = (self.flags & FLAG_TERMINATED) != 0
+        return self._done
+
+    @property
+    def truncated(self):
+        if self._truncated is None:
+            self._truncated = (self.flags & FLAG_TRUNCATED) != 0
+        return self._truncated
+
+    def __iter__(self):  # state, reward, done, truncated = env.step(a)
+        return iter((self.state, self.reward, self.done, self.truncated))
+
+
+class _DeviceArray:
+    """Zero-copy torch view of memory the C library owns (CUDA array interface)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
 Rollout = namedtuple("Rollout", ["obs", "reward", "flags", "done_count"])
 EpisodeStats = namedtuple("EpisodeStats", ["episodes", "terminated", "truncated", "length_sum", "return_sum"])
 
@@ -75,12 +108,20 @@ class GpuVecEnv:
         self._act_space = spaces.action_space(self.kind)
         n = self.num_envs
         with torch.cuda.device(self.device):
-            self._obs = torch.empty((self.obs_dim, n), dtype=torch.float32, device=self.device)
             self._reward = torch.empty(n, dtype=torch.float32, device=self.device)
             self._flags = torch.empty(n, dtype=torch.uint8, device=self.device)
+            # the resident state rows [state_dim, N] as a tensor (valid while this env is open)
+            self.state_view = torch.as_tensor(_DeviceArray(self._lib.mgym_state_ptr(self._h), (self.state_dim, n)),
+                                              device=self.device)
+            # kinds whose observation IS the state (CartPole, MountainCar, MountainCarContinuous) return that view:
+            # no separate observation buffer is written (42 instead of 58 bytes per CartPole env-step)
+            self.obs_is_state = self.kind in (CARTPOLE, MOUNTAIN_CAR, MOUNTAIN_CAR_CONTINUOUS)
+            self._obs = self.state_view if self.obs_is_state else torch.empty((self.obs_dim, n), dtype=torch.float32,
+                                                                              device=self.device)
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
+        """Frees the handle; `state_view` (and observations returned for obs_is_state kinds) dangle afterwards."""
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.mgym_destroy(self._h)
             self._h = C.c_void_p()
@@ -104,11 +145,12 @@ class GpuVecEnv:
     def reset(self, mask=None, out=None):
         """Gym::reset for all envs (or those with mask != 0).  Returns obs [obs_dim, N]."""
         obs = self._obs if out is None else out
+        dst = None if (self.obs_is_state and out is None) else _ptr(obs)
         if mask is None:
-            _lib.check(self._lib.mgym_reset(self._h, _ptr(obs), self._stream()))
+            _lib.check(self._lib.mgym_reset(self._h, dst, self._stream()))
         else:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-            _lib.check(self._lib.mgym_reset_masked(self._h, _ptr(mask), _ptr(obs), self._stream()))
+            _lib.check(self._lib.mgym_reset_masked(self._h, _ptr(mask), dst, self._stream()))
         return obs
 
     def _check_actions(self, actions, lead=()):
@@ -129,10 +171,9 @@ class GpuVecEnv:
         final = None
         if want_final_obs:
             final = torch.empty_like(self._obs)
-        _lib.check(self._lib.mgym_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._flags),
-                                       _ptr(final), self._stream()))
-        info = StepInfo(self._obs, self._reward, (self._flags & FLAG_TERMINATED) != 0,
-                        (self._flags & FLAG_TRUNCATED) != 0)
+        _lib.check(self._lib.mgym_step(self._h, _ptr(actions), None if self.obs_is_state else _ptr(self._obs),
+                                       _ptr(self._reward), _ptr(self._flags), _ptr(final), self._stream()))
+        info = StepInfo(self._obs, self._reward, self._flags)
         return (info, final) if want_final_obs else info
 
     def step_raw(self, actions, obs_out=None, reward_out=None, flags_out=None, final_obs_out=None):
