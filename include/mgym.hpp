@@ -131,9 +131,13 @@ class GpuVecEnv {
     check(mgym_reset_masked(h_, mask_device, obs_, stream_));
     return obs_;
   }
+  // For kinds whose observation is the state (CartPole, MountainCar, MountainCarContinuous) StepInfo.state is
+  // the resident state rows themselves: no separate observation buffer is written.
+  bool obs_is_state() const { return mgym_obs_dim(kind_) == mgym_state_dim(kind_); }
   StepInfo step(const void* actions_device) {  // cartpole.rs:251-348
-    check(mgym_step(h_, actions_device, obs_, reward_, flags_, nullptr, stream_));
-    return StepInfo{obs_, reward_, flags_};
+    const bool alias = obs_is_state();
+    check(mgym_step(h_, actions_device, alias ? nullptr : obs_, reward_, flags_, nullptr, stream_));
+    return StepInfo{alias ? mgym_state_ptr(h_) : obs_, reward_, flags_};
   }
   BoxSpace observation_space() const {  // cartpole.rs:350-352
     BoxSpace b{std::vector<float>(obs_dim()), std::vector<float>(obs_dim())};

@@ -176,6 +176,30 @@ static void test_batched_against_oracle() {
   }
 }
 
+// Gym::step on device buffers: the zero-copy observation of obs-is-state kinds equals mgym_get_obs
+static void test_device_step_zero_copy() {
+  const uint64_t n = 4096;
+  auto env = mgym::GpuVecEnv::builder(MGYM_CARTPOLE_V1, n).seed(3).build();
+  env.reset();
+  unsigned char* acts = nullptr;
+  float* obs = nullptr;
+  cudaMalloc(reinterpret_cast<void**>(&acts), n);
+  cudaMalloc(reinterpret_cast<void**>(&obs), sizeof(float) * 4 * n);
+  for (int t = 0; t < 20; ++t) {
+    env.sample_actions(acts);
+    mgym::StepInfo info = env.step(acts);
+    CHECK(info.state == mgym_state_ptr(env.handle()), "CartPole observation must alias the state rows");
+    mgym::check(mgym_get_obs(env.handle(), obs, nullptr));
+    std::vector<float> a(4 * n), b(4 * n);
+    cudaMemcpy(a.data(), info.state, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(b.data(), obs, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+    CHECK(std::memcmp(a.data(), b.data(), sizeof(float) * 4 * n) == 0, "step %d: zero-copy obs differs from get_obs", t);
+  }
+  cudaFree(acts);
+  cudaFree(obs);
+  std::printf("ok   Gym::step on device buffers (zero-copy observation)\n");
+}
+
 int main(int argc, char** argv) {
   const std::string golden = argc > 1 ? argv[1] : "tests/golden";
   try {
@@ -184,6 +208,7 @@ int main(int argc, char** argv) {
     test_cartpole();
     test_mountain_car();
     test_invalid_action();
+    test_device_step_zero_copy();
     test_batched_against_oracle();
   } catch (const std::exception& e) {
     std::fprintf(stderr, "FAIL exception: %s\n", e.what());
