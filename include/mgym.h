@@ -24,8 +24,9 @@
  *   reward        float[N]
  *   flags         uint8_t[N]; bit0 = StepInfo.done (terminated), bit1 = StepInfo.truncated
  *   trajectories  time-major: obs[k][c][N], reward[k][N], flags[k][N], actions[k][N]
- * The 128-bit vector path needs N % 4 == 0 and 16-byte aligned pointers; anything else
- * takes the scalar-lane instantiation of the same kernel (same results, slower).
+ * Fastest path (TMA-staged step kernel): auto_reset, N % 1024 == 0, 16-byte aligned pointers.
+ * N % 4 == 0 with aligned pointers takes the 128-bit vector kernel, anything else the
+ * scalar-lane instantiation of the same kernel: same results bit for bit, lower throughput.
  *
  * Semantics
  * ---------

@@ -1,13 +1,15 @@
 // mgym_kernels.cuh -- the two kernel modes of the hot path.
 //
-//   step_kernel     one Gym::step per env per launch: SoA state rows are read and rewritten with
-//                   128-bit accesses (one thread = V consecutive envs), actions / reward / flags /
-//                   step counters are packed vector accesses.  HBM-bound by construction.
+//   step_kernel_tma one Gym::step per env per launch, the headline form: a producer warp stages 1024-env
+//                   tiles (state rows, actions, counters) into a shared-memory ring with cp.async.bulk,
+//                   eight consumer warps step 4 consecutive envs per thread and store with 128-bit
+//                   stores.  HBM-bound (profiles/README.md).
+//   step_kernel     the same step with plain vector loads: manual mode, ragged N, unaligned buffers.
 //   rollout_kernel  K fused steps: state and counters stay in registers, only the trajectory
 //                   (obs / reward / flags) is written, actions are read or drawn from Philox.
 //
-// Both are persistent grid-stride kernels (grid = multiple of the SM count) so the episode
-// statistics reduce to one set of atomics per CTA.
+// All are persistent kernels (grid sized from the SM count) so the episode statistics reduce to one
+// set of atomics per CTA.  The per-env work is shared: step_group().
 #pragma once
 
 #include "mgym_device.cuh"
