@@ -88,6 +88,7 @@ SYMBOLS = {
 PROBES = {
     "mgym_probe_trig": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "mgym_probe_philox": (_i, [_vp, _vp, _u64, _vp]),
+    "mgym_probe_trig_checksum": (_i, [C.c_uint32, _u64, C.c_uint32, _vp]),
     "mgym_probe_fast_exhaustive": (_i, [_i, _u64, _u64, _vp]),
     "mgym_probe_fast_div_random": (_i, [_u64, _u64, _vp]),
 }

@@ -915,6 +915,19 @@ int mgym_probe_fast_div_random(uint64_t seed, uint64_t n, uint64_t* out2) {
   return MGYM_OK;
 }
 
+int mgym_probe_trig_checksum(uint32_t first, uint64_t count, uint32_t stride, uint64_t* out) {
+  unsigned long long* d = nullptr;
+  MGYM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+  MGYM_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+  trig_checksum_kernel<<<148 * 8, 256>>>(first, count, stride, d);
+  MGYM_CUDA(cudaGetLastError());
+  unsigned long long h = 0;
+  MGYM_CUDA(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *out = h;
+  return MGYM_OK;
+}
+
 int mgym_probe_philox(const uint32_t* ctr_key, uint32_t* out, uint64_t n, void* stream) {
   philox_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctr_key, out, n);
   MGYM_CUDA(cudaGetLastError());

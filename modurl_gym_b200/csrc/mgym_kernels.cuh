@@ -998,6 +998,36 @@ __global__ void fast_div_random_kernel(uint64_t seed, uint64_t n, unsigned long 
   if (my_bad) atomicAdd(bad, my_bad);
 }
 
+// digest of (x, sin x, cos x) from sincos_ref over magnitudes first, first+stride, ... and both signs: the same
+// order-independent sum as oracle_trig_checksum (tests/test_gpu_trig_exhaustive.py)
+__device__ __forceinline__ unsigned long long trig_mix(uint32_t xb, uint32_t sb, uint32_t cb) {
+  unsigned long long h = ((unsigned long long)sb << 32) | cb;
+  h ^= (unsigned long long)xb * 0x9E3779B97F4A7C15ull;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return h;
+}
+__global__ void trig_checksum_kernel(uint32_t first, uint64_t count, uint32_t stride, unsigned long long* out) {
+  unsigned long long sum = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t mag = first + (uint32_t)(i * stride);
+#pragma unroll
+    for (uint32_t sign = 0; sign < 2; ++sign) {
+      const uint32_t xb = mag | (sign << 31);
+      float s, c;
+      sincos_ref(__uint_as_float(xb), s, c);
+      sum += trig_mix(xb, __float_as_uint(s), __float_as_uint(c));
+      // the single-result forms must agree with the pair
+      if (__float_as_uint(sin_ref(__uint_as_float(xb))) != __float_as_uint(s) ||
+          __float_as_uint(cos_ref(__uint_as_float(xb))) != __float_as_uint(c))
+        sum += 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, sum);
+}
+
 __global__ void philox_probe_kernel(const uint32_t* ctr_key, uint32_t* out, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

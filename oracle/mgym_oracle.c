@@ -152,6 +152,65 @@ static inline float ref_cosf(float x) { return sincos_eval(x, 1); }
 ORACLE_HOT float oracle_sinf(float x) { return ref_sinf(x); }
 ORACLE_HOT float oracle_cosf(float x) { return ref_cosf(x); }
 
+/* Order-independent 64-bit digest of (x, sin x, cos x) over the bit patterns first, first+stride, ... (count of
+ * them, both signs): lets the device be compared with this restatement over the WHOLE domain without moving
+ * 2^32 results around (tests/test_gpu_trig_exhaustive.py; the device computes the same sum with atomics). */
+static inline uint64_t trig_mix(uint32_t xb, uint32_t sb, uint32_t cb) {
+  uint64_t h = ((uint64_t)sb << 32) | cb;
+  h ^= (uint64_t)xb * 0x9E3779B97F4A7C15ull;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return h;
+}
+
+typedef struct {
+  uint32_t first, stride;
+  uint64_t count, sum;
+} trig_job;
+
+ORACLE_HOT static void trig_checksum_run(trig_job *j) {
+  uint64_t sum = 0;
+  for (uint64_t i = 0; i < j->count; ++i) {
+    const uint32_t mag = j->first + (uint32_t)(i * j->stride);
+    for (uint32_t sign = 0; sign < 2; ++sign) {
+      const uint32_t xb = mag | (sign << 31);
+      float x;
+      memcpy(&x, &xb, 4);
+      const float sv = ref_sinf(x), cv = ref_cosf(x);
+      sum += trig_mix(xb, f32_bits(sv), f32_bits(cv));
+    }
+  }
+  j->sum = sum;
+}
+static void *trig_checksum_thread(void *arg) {
+  trig_checksum_run((trig_job *)arg);
+  return NULL;
+}
+
+uint64_t oracle_trig_checksum(uint32_t first_bits, uint64_t count, uint32_t stride, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  trig_job jobs[256];
+  pthread_t th[256];
+  const uint64_t per = (count + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    uint64_t a = per * t, b = a + per;
+    if (a > count) a = count;
+    if (b > count) b = count;
+    jobs[t].first = first_bits + (uint32_t)(a * stride);
+    jobs[t].stride = stride;
+    jobs[t].count = b - a;
+    jobs[t].sum = 0;
+    pthread_create(&th[t], NULL, trig_checksum_thread, &jobs[t]);
+  }
+  uint64_t sum = 0;
+  for (int t = 0; t < n_threads; ++t) {
+    pthread_join(th[t], NULL);
+    sum += jobs[t].sum;
+  }
+  return sum;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11; Random123 constants)    */
 /* ------------------------------------------------------------------------- */

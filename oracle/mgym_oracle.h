@@ -76,6 +76,9 @@ int oracle_action_is_continuous(int kind);
 float oracle_sinf(float x);
 float oracle_cosf(float x);
 
+/* digest of (x, sin x, cos x) over magnitudes first, first+stride, ... and both signs (exhaustive device check) */
+uint64_t oracle_trig_checksum(uint32_t first_bits, uint64_t count, uint32_t stride, int n_threads);
+
 /* Philox4x32-10 */
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* reset state of global env g for (tag, t); tag 0 = auto-reset at step t, 1 = explicit reset number t */

@@ -66,6 +66,8 @@ def lib():
         L.oracle_sinf.argtypes = [C.c_float]
         L.oracle_cosf.restype = C.c_float
         L.oracle_cosf.argtypes = [C.c_float]
+        L.oracle_trig_checksum.restype = C.c_uint64
+        L.oracle_trig_checksum.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_int]
         L.oracle_config_default.argtypes = [C.c_int, C.POINTER(Config)]
         L.oracle_env_step.restype = C.c_uint32
         L.oracle_env_step.argtypes = [C.c_int, C.POINTER(Config), C.c_void_p, C.POINTER(C.c_uint32),
@@ -107,6 +109,10 @@ def sinf(x):
 
 def cosf(x):
     return lib().oracle_cosf(float(np.float32(x)))
+
+
+def trig_checksum(first_bits, count, stride=1, threads=None):
+    return lib().oracle_trig_checksum(first_bits, count, stride, threads or (os.cpu_count() or 1))
 
 
 def philox(ctr, key):
