@@ -159,6 +159,8 @@ KernelParams base_params(const mgym_env* e) {
   p.stats = (e->cfg.auto_reset && e->cfg.track_stats) ? e->stats : nullptr;
   p.bad_action = e->cfg.validate_actions ? e->bad_action : nullptr;
   p.n = e->n;
+  p.first = 0;
+  p.ld = e->n;
   p.seed = e->seed;
   p.env_base = e->cfg.env_index_base;
   p.t = e->t;
@@ -263,6 +265,16 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
           default: return launch_step_tma<KIND, CNT_U32>(e, p, st);
         }
       }
+    }
+    if (autor && use_tma() && p.first == 0 && p.n > TMA_TILE) {
+      // ragged size: whole 1024-env tiles on the TMA kernel, the remaining (< 1024) envs on the vector kernel
+      KernelParams head = p, tail = p;
+      head.n = p.n - p.n % TMA_TILE;
+      tail.first = head.n;
+      tail.n = p.n - head.n;
+      int rc = dispatch_mode<KIND, 4, false>(e, head, st);
+      if (rc != MGYM_OK) return rc;
+      return dispatch_mode<KIND, 4, false>(e, tail, st);
     }
   }
 #define MGYM_LAUNCH(AUTO_, CNT_)                                                                         \

@@ -50,7 +50,10 @@ struct KernelParams {
   unsigned long long* stats;
   unsigned long long* done_count;  // rollout: finished env-steps
   uint32_t* bad_action;            // validate_actions: set to 1 on an out-of-range discrete action
-  uint64_t n, seed, env_base, t;
+  uint64_t n;      // envs covered by this launch
+  uint64_t first;  // index (within the handle) of the first of them
+  uint64_t ld;     // row stride of every SoA buffer = envs in the handle
+  uint64_t seed, env_base, t;
   uint32_t K;
   EnvConsts k;
 };
@@ -316,13 +319,13 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
   const bool want_final = p.final_obs_out != nullptr;
 
   for (uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; grp < groups; grp += stride) {
-    const uint64_t base = grp * V;
+    const uint64_t base = p.first + grp * V;
     Group<KIND, V> g;
     act_t action[V];
     {
       Vec<float, V> s[SD];
 #pragma unroll
-      for (int c = 0; c < SD; ++c) s[c] = ldv<float, V>(p.state + (uint64_t)c * p.n + base);
+      for (int c = 0; c < SD; ++c) s[c] = ldv<float, V>(p.state + (uint64_t)c * p.ld + base);
       const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(p.actions) + base);
       Vec<cnt_t, V> cnt;
       if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
       for (int c = 0; c < SD; ++c) {
 #pragma unroll
         for (int v = 0; v < V; ++v) s[c].v[v] = g.st[v][c];
-        stv<float, V>(p.state + (uint64_t)c * p.n + base, s[c]);
+        stv<float, V>(p.state + (uint64_t)c * p.ld + base, s[c]);
       }
     }
     if constexpr (CNT != CNT_NONE) {
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
         Vec<float, V> o;
 #pragma unroll
         for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-        stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+        stv<float, V>(p.obs_out + (uint64_t)c * p.ld + base, o);
       }
     }
     if (want_final) {
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
         Vec<float, V> o;
 #pragma unroll
         for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
-        stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+        stv<float, V>(p.final_obs_out + (uint64_t)c * p.ld + base, o);
       }
     }
     if (p.reward_out) {
@@ -523,10 +526,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
         tma::mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);  // first round passes at once
         const uint32_t bar = full0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
-        const uint64_t e0 = tile * TMA_TILE;
+        const uint64_t e0 = p.first + tile * TMA_TILE;
         tma::mbar_expect_tx(bar, tx);
 #pragma unroll
-        for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.n + e0, L::ROW, bar);
+        for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.ld + e0, L::ROW, bar);
         tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
         if constexpr (CNT != CNT_NONE)
           tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
-      const uint64_t base = tile * TMA_TILE + tid * V;
+      const uint64_t base = p.first + tile * TMA_TILE + tid * V;
       tma::mbar_wait(full0 + 8 * s, parity);
 
       Group<KIND, V> g;
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         Vec<float, V> o;
 #pragma unroll
         for (int v = 0; v < V; ++v) o.v[v] = g.st[v][c];
-        stv<float, V>(p.state + (uint64_t)c * p.n + base, o);
+        stv<float, V>(p.state + (uint64_t)c * p.ld + base, o);
       }
       if constexpr (CNT != CNT_NONE) {
         Vec<cnt_t, V> cnt;
@@ -619,7 +622,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
           Vec<float, V> o;
 #pragma unroll
           for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-          stv<float, V>(p.obs_out + (uint64_t)c * p.n + base, o);
+          stv<float, V>(p.obs_out + (uint64_t)c * p.ld + base, o);
         }
       }
       if (want_final) {
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
           Vec<float, V> o;
 #pragma unroll
           for (int v = 0; v < V; ++v) o.v[v] = g.fin[v][c];
-          stv<float, V>(p.final_obs_out + (uint64_t)c * p.n + base, o);
+          stv<float, V>(p.final_obs_out + (uint64_t)c * p.ld + base, o);
         }
       }
       if (p.reward_out) {
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
   for (uint64_t grp0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); grp0 < groups; grp0 += stride) {
     const uint64_t grp = grp0 + lane;
     const bool active = grp < groups;
-    const uint64_t base = active ? grp * V : 0;
+    const uint64_t base = p.first + (active ? grp * V : 0);
     Group<KIND, V> g;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
     if (active) {
 #pragma unroll
       for (int c = 0; c < SD; ++c) {
-        const Vec<float, V> s = ldv<float, V>(p.state + (uint64_t)c * p.n + base);
+        const Vec<float, V> s = ldv<float, V>(p.state + (uint64_t)c * p.ld + base);
 #pragma unroll
         for (int v = 0; v < V; ++v) g.st[v][c] = s.v[v];
       }
@@ -718,11 +721,11 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
     }
 
     // running output pointers: one 64-bit add per array per step instead of a multiply-add chain per store
-    const uint64_t obs_step = (uint64_t)OD * p.n;
+    const uint64_t obs_step = (uint64_t)OD * p.ld;
     float* obs_ptr = p.obs_out ? p.obs_out + base : nullptr;
     float* rew_ptr = p.reward_out ? p.reward_out + base : nullptr;
     uint8_t* flg_ptr = p.flags_out ? p.flags_out + base : nullptr;
-    const act_t* act_ptr = actions ? actions + base + p.n : nullptr;  // next step's row
+    const act_t* act_ptr = actions ? actions + base + p.ld : nullptr;  // next step's row
 
     for (uint32_t kk = 0; kk < p.K; ++kk) {
       const uint64_t t = p.t + kk;
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
       // prefetch the next step's actions first: the load stays in flight for the whole step
       if (!policy && active && kk + 1 < p.K) {
         a_next.load(act_ptr);
-        act_ptr += p.n;
+        act_ptr += p.ld;
       }
       act_t action[V];
       if (policy) {
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
             Vec<float, V> o;
 #pragma unroll
             for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-            stv<float, V>(obs_ptr + (uint64_t)c * p.n, o);
+            stv<float, V>(obs_ptr + (uint64_t)c * p.ld, o);
           }
           obs_ptr += obs_step;
         }
@@ -779,14 +782,14 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
 #pragma unroll
           for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
           stv<float, V>(rew_ptr, rw);
-          rew_ptr += p.n;
+          rew_ptr += p.ld;
         }
         if (flg_ptr) {
           Vec<uint8_t, V> fl;
 #pragma unroll
           for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
           stv<uint8_t, V>(flg_ptr, fl);
-          flg_ptr += p.n;
+          flg_ptr += p.ld;
         }
       }
     }
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
         Vec<float, V> s;
 #pragma unroll
         for (int v = 0; v < V; ++v) s.v[v] = g.st[v][c];
-        stv<float, V>(p.state + (uint64_t)c * p.n + base, s);
+        stv<float, V>(p.state + (uint64_t)c * p.ld + base, s);
       }
       if constexpr (CNT != CNT_NONE) {
         Vec<cnt_t, V> cnt;
@@ -838,16 +841,17 @@ template <int KIND, int CNT>
 __global__ void reset_kernel(const KernelParams p, const uint8_t* mask, uint64_t reset_index) {
   using E = Env<KIND>;
   using cnt_t = typename CounterType<CNT>::type;
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.n) return;
+  const uint64_t i = p.first + j;
   float st[E::SD], obs[E::OD];
   if (mask && !mask[i]) {
     if (p.obs_out) {
 #pragma unroll
-      for (int c = 0; c < E::SD; ++c) st[c] = p.state[(uint64_t)c * p.n + i];
+      for (int c = 0; c < E::SD; ++c) st[c] = p.state[(uint64_t)c * p.ld + i];
       E::obs(st, obs);
 #pragma unroll
-      for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.n + i] = obs[c];
+      for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.ld + i] = obs[c];
     }
     return;
   }
@@ -860,14 +864,14 @@ __global__ void reset_kernel(const KernelParams p, const uint8_t* mask, uint64_t
     E::reset(philox_env(p.seed, g, reset_index, TAG_RESET), st);
   }
 #pragma unroll
-  for (int c = 0; c < E::SD; ++c) p.state[(uint64_t)c * p.n + i] = st[c];
+  for (int c = 0; c < E::SD; ++c) p.state[(uint64_t)c * p.ld + i] = st[c];
   if constexpr (CNT != CNT_NONE) reinterpret_cast<cnt_t*>(p.steps)[i] = 0;  // cartpole.rs:243
   if (p.sbt) p.sbt[i] = SBT_NONE;                                            // cartpole.rs:239
   if (p.ep_return) p.ep_return[i] = 0.0f;
   if (p.obs_out) {
     E::obs(st, obs);
 #pragma unroll
-    for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.n + i] = obs[c];
+    for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.ld + i] = obs[c];
   }
 }
 

@@ -250,7 +250,7 @@ def run_auto_parity(gym, oracle, kind, n, T, seed, use_pool=False, want_final=Fa
 
 
 @pytest.mark.parametrize("kind", range(5))
-@pytest.mark.parametrize("n", [2048, 1027])
+@pytest.mark.parametrize("n", [2048, 1027, 3076])  # whole TMA tiles; ragged scalar lanes; 3 tiles + a 4-env tail
 def test_auto_reset_parity(gym, oracle, kind, n):
     T = {0: 600, 1: 300, 2: 300, 3: 250, 4: 200}[kind]
     s = run_auto_parity(gym, oracle, kind, n, T, seed=0x5EED)
