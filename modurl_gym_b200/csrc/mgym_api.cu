@@ -46,6 +46,8 @@ struct mgym_env {
   float* h_obs = nullptr;
   float* h_reward = nullptr;
   uint8_t* h_flags = nullptr;
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -266,11 +268,11 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
         }
       }
     }
-    if (autor && use_tma() && p.first == 0 && p.n > TMA_TILE) {
+    if (autor && use_tma() && p.n > TMA_TILE) {
       // ragged size: whole 1024-env tiles on the TMA kernel, the remaining (< 1024) envs on the vector kernel
       KernelParams head = p, tail = p;
       head.n = p.n - p.n % TMA_TILE;
-      tail.first = head.n;
+      tail.first = p.first + head.n;
       tail.n = p.n - head.n;
       int rc = dispatch_mode<KIND, 4, false>(e, head, st);
       if (rc != MGYM_OK) return rc;
@@ -437,6 +439,10 @@ int mgym_destroy(mgym_env* e) {
   cudaFree(e->h_obs);
   cudaFree(e->h_reward);
   cudaFree(e->h_flags);
+  for (auto& s : e->pipe_stream)
+    if (s) cudaStreamDestroy(s);
+  for (auto& ev : e->pipe_event)
+    if (ev) cudaEventDestroy(ev);
   delete e;
   return MGYM_OK;
 }
@@ -810,26 +816,68 @@ int mgym_sample_actions(mgym_env* e, void* actions_out, void* stream) {
   return MGYM_OK;
 }
 
+// Host-buffer step.  Large batches are cut into chunks of whole 1024-env tiles that alternate between two
+// internal streams, so the D2H of chunk c overlaps the H2D and the kernel of chunk c+1 (PCIe is full duplex):
+// the call then costs about the D2H time alone.  Every chunk is one sub-range launch of the ordinary step.
 int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float* reward_host, uint8_t* flags_host,
                    void* stream) {
   if (!e || !actions_host) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_step_host: NULL argument");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->n;
-  const size_t asz = action_size(e->kind) * n, osz = sizeof(float) * kObsDim[e->kind] * n;
+  const int od = kObsDim[e->kind];
+  const size_t act = action_size(e->kind), asz = act * n, osz = sizeof(float) * od * n;
+  const bool obs_is_state = kObsDim[e->kind] == kStateDim[e->kind];
   if (!e->h_actions) MGYM_CUDA(cudaMalloc(&e->h_actions, asz));
-  if (obs_host && !e->h_obs) MGYM_CUDA(cudaMalloc(&e->h_obs, osz));
+  if (obs_host && !obs_is_state && !e->h_obs) MGYM_CUDA(cudaMalloc(&e->h_obs, osz));
   if (reward_host && !e->h_reward) MGYM_CUDA(cudaMalloc(&e->h_reward, sizeof(float) * n));
   if (flags_host && !e->h_flags) MGYM_CUDA(cudaMalloc(&e->h_flags, n));
-  MGYM_CUDA(cudaMemcpyAsync(e->h_actions, actions_host, asz, cudaMemcpyHostToDevice, st));
-  int rc = mgym_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, reward_host ? e->h_reward : nullptr,
-                     flags_host ? e->h_flags : nullptr, nullptr, stream);
-  if (rc != MGYM_OK) return rc;
-  if (obs_host) MGYM_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, osz, cudaMemcpyDeviceToHost, st));
-  if (reward_host) MGYM_CUDA(cudaMemcpyAsync(reward_host, e->h_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-  if (flags_host) MGYM_CUDA(cudaMemcpyAsync(flags_host, e->h_flags, n, cudaMemcpyDeviceToHost, st));
+  // observations of obs-is-state kinds are read straight out of the resident state rows
+  float* dev_obs = obs_host ? (obs_is_state ? e->state : e->h_obs) : nullptr;
+
+  constexpr size_t kMinChunk = 1u << 18;  // envs; below 2 chunks the plain path is used
+  const size_t chunks = (n >= 2 * kMinChunk && e->vec4) ? (n / kMinChunk > 8 ? 8 : n / kMinChunk) : 1;
+  if (chunks > 1 && !e->pipe_stream[0]) {
+    for (auto& s : e->pipe_stream) MGYM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& ev : e->pipe_event) MGYM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  if (chunks > 1) {
+    MGYM_CUDA(cudaEventRecord(e->pipe_event[2], st));
+    for (auto& s : e->pipe_stream) MGYM_CUDA(cudaStreamWaitEvent(s, e->pipe_event[2], 0));
+  }
+  const size_t per = ((n / chunks) / TMA_TILE) * TMA_TILE;
+  for (size_t c = 0; c < chunks; ++c) {
+    cudaStream_t cs = chunks > 1 ? e->pipe_stream[c & 1] : st;
+    const size_t b = c * per, cnt = (c + 1 == chunks) ? n - b : per;
+    MGYM_CUDA(cudaMemcpyAsync((uint8_t*)e->h_actions + act * b, (const uint8_t*)actions_host + act * b, act * cnt,
+                              cudaMemcpyHostToDevice, cs));
+    KernelParams p = base_params(e);
+    p.first = b;
+    p.n = cnt;
+    p.actions = e->h_actions;
+    p.obs_out = (obs_host && !obs_is_state) ? e->h_obs : nullptr;
+    p.reward_out = reward_host ? e->h_reward : nullptr;
+    p.flags_out = flags_host ? e->h_flags : nullptr;
+    int rc = dispatch<false>(e, p, e->vec4, cs);
+    if (rc != MGYM_OK) return rc;
+    if (obs_host) {
+      for (int r = 0; r < od; ++r)
+        MGYM_CUDA(cudaMemcpyAsync(obs_host + (size_t)r * n + b, dev_obs + (size_t)r * n + b, sizeof(float) * cnt,
+                                  cudaMemcpyDeviceToHost, cs));
+    }
+    if (reward_host)
+      MGYM_CUDA(cudaMemcpyAsync(reward_host + b, e->h_reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, cs));
+    if (flags_host) MGYM_CUDA(cudaMemcpyAsync(flags_host + b, e->h_flags + b, cnt, cudaMemcpyDeviceToHost, cs));
+  }
+  if (chunks > 1) {
+    for (int i = 0; i < 2; ++i) {
+      MGYM_CUDA(cudaEventRecord(e->pipe_event[i], e->pipe_stream[i]));
+      MGYM_CUDA(cudaStreamWaitEvent(st, e->pipe_event[i], 0));
+    }
+  }
+  e->t += 1;
   MGYM_CUDA(cudaStreamSynchronize(st));
-  return MGYM_OK;
+  return check_bad_action(e, st);
 }
 
 // ---------------------------------------------------------------------------------------------

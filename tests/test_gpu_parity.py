@@ -577,3 +577,29 @@ def test_mountain_car_1000_step_chunked_rollout(gym, oracle):
     assert total_done == dones and env.step_index == T
     state, steps, _ = env.get_state()
     assert_bit_equal(host(state), ref.state, "final state")
+
+
+@pytest.mark.parametrize("kind", [0, 3])
+def test_step_host_pipelined_chunks_equal_plain_step(gym, kind):
+    """mgym_step_host cuts large batches into chunks on two internal streams (H2D / kernel / D2H overlap); the
+    result must equal the ordinary device-buffer step bit for bit, including a ragged last chunk."""
+    n = (1 << 20) + 3 * 1024 + 8
+    a_env, b_env = gym.GpuVecEnv(kind, n, seed=12), gym.GpuVecEnv(kind, n, seed=12)
+    a_env.reset(), b_env.reset()
+    od = a_env.obs_dim
+    obs = torch.empty((od, n)).pin_memory()
+    rew = torch.empty(n).pin_memory()
+    flg = torch.empty(n, dtype=torch.uint8).pin_memory()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    for t in range(25):
+        if a_env.continuous:
+            acts = torch.rand(n, device="cuda", generator=gen) * 4 - 2
+        else:
+            acts = torch.randint(0, 2, (n,), dtype=torch.uint8, device="cuda", generator=gen)
+        a_env.step_host(acts.cpu().pin_memory(), obs, rew, flg)
+        info = b_env.step(acts)
+        assert torch.equal(obs.cuda().view(torch.int32), info.state.view(torch.int32)), f"obs differ at step {t}"
+        assert torch.equal(rew.cuda().view(torch.int32), info.reward.view(torch.int32))
+        assert torch.equal(flg.cuda(), info.flags)
+    assert a_env.stats() == b_env.stats() and a_env.step_index == b_env.step_index
