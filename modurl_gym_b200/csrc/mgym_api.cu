@@ -46,6 +46,9 @@ struct mgym_env {
   float* h_obs = nullptr;
   float* h_reward = nullptr;
   uint8_t* h_flags = nullptr;
+  unsigned long long* work = nullptr;   // 3 ticket counters: caller's stream, pipe stream 0, pipe stream 1
+  uint64_t work_issued[3] = {0, 0, 0};  // tickets handed to launches so far, per counter
+  int work_slot = 0;                    // counter the next TMA launch uses
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
 };
@@ -203,7 +206,9 @@ int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, u
 
 // TMA-staged step kernel (auto-reset, vector path, N a multiple of the 128-env warp tile)
 template <int KIND, int CNT>
-int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
+int launch_step_tma(const mgym_env* ce, const KernelParams& p_in, cudaStream_t st) {
+  mgym_env* e = const_cast<mgym_env*>(ce);  // ticket accounting
+  KernelParams p = p_in;
   using L = TmaLayout<KIND, CNT>;
   auto kernel = step_kernel_tma<KIND, CNT>;
   constexpr int threads = TMA_THREADS;
@@ -217,14 +222,14 @@ int launch_step_tma(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
     if (e->device < kMaxDevices) cached_per_sm[e->device] = per_sm;
   }
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
-  // Static round-robin tiles: every CTA runs ceil(tiles / grid) rounds, so use the SMALLEST grid that
-  // still needs the same number of rounds as the full machine -- the last round is then nearly full
-  // (2^24 envs: 16384 tiles, 296 slots -> 56 rounds -> 293 CTAs, 99.9 % balanced instead of 98.8 %).
+  // persistent CTAs, tiles handed out by tickets (see the producer warp)
   const uint64_t slots = (uint64_t)e->num_sms * per_sm;
   const uint64_t tiles = p.n / TMA_TILE;
-  const uint64_t rounds = (tiles + slots - 1) / slots;
-  uint64_t blocks = (tiles + rounds - 1) / rounds;
+  uint64_t blocks = tiles < slots ? tiles : slots;
   if (blocks < 1) blocks = 1;
+  p.work_counter = e->work + e->work_slot;
+  p.work_base = e->work_issued[e->work_slot];
+  e->work_issued[e->work_slot] += tiles + blocks;
   static const bool pdl = [] {
     const char* s = getenv("MGYM_NO_PDL");
     return !(s && atoi(s) != 0);
@@ -439,6 +444,7 @@ int mgym_destroy(mgym_env* e) {
   cudaFree(e->h_obs);
   cudaFree(e->h_reward);
   cudaFree(e->h_flags);
+  cudaFree(e->work);
   for (auto& s : e->pipe_stream)
     if (s) cudaStreamDestroy(s);
   for (auto& ev : e->pipe_event)
@@ -519,6 +525,8 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
     }
     MGYM_CUDA(cudaMalloc(&e->stats, 5 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMemset(e->stats, 0, 5 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMalloc(&e->work, 3 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMemset(e->work, 0, 3 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMalloc(&e->bad_action, sizeof(uint32_t)));
     MGYM_CUDA(cudaMemset(e->bad_action, 0, sizeof(uint32_t)));
     MGYM_CUDA(cudaDeviceSynchronize());
@@ -760,6 +768,7 @@ int mgym_checkpoint_load(mgym_env* e, const void* blob, size_t blob_bytes, void*
 int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_out, uint8_t* flags_out,
               float* final_obs_out, void* stream) {
   if (!e || !actions) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_step: NULL argument");
+  e->work_slot = 0;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   KernelParams p = base_params(e);
@@ -848,6 +857,7 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
   const size_t per = ((n / chunks) / TMA_TILE) * TMA_TILE;
   for (size_t c = 0; c < chunks; ++c) {
     cudaStream_t cs = chunks > 1 ? e->pipe_stream[c & 1] : st;
+    e->work_slot = chunks > 1 ? 1 + (int)(c & 1) : 0;
     const size_t b = c * per, cnt = (c + 1 == chunks) ? n - b : per;
     MGYM_CUDA(cudaMemcpyAsync((uint8_t*)e->h_actions + act * b, (const uint8_t*)actions_host + act * b, act * cnt,
                               cudaMemcpyHostToDevice, cs));
@@ -875,6 +885,7 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
       MGYM_CUDA(cudaStreamWaitEvent(st, e->pipe_event[i], 0));
     }
   }
+  e->work_slot = 0;
   e->t += 1;
   MGYM_CUDA(cudaStreamSynchronize(st));
   return check_bad_action(e, st);

@@ -50,6 +50,8 @@ struct KernelParams {
   unsigned long long* stats;
   unsigned long long* done_count;  // rollout: finished env-steps
   uint32_t* bad_action;            // validate_actions: set to 1 on an out-of-range discrete action
+  unsigned long long* work_counter;  // TMA step kernel: tile tickets (monotonic across launches)
+  uint64_t work_base;                // first ticket of this launch
   uint64_t n;      // envs covered by this launch
   uint64_t first;  // index (within the handle) of the first of them
   uint64_t ld;     // row stride of every SoA buffer = envs in the handle
@@ -475,7 +477,8 @@ struct TmaLayout {
   static constexpr uint32_t OFF_RET = OFF_CNT + CNT_BYTES;
   static constexpr uint32_t RET_BYTES = E::ANALYTIC_RETURN ? 0 : ROW;
   static constexpr uint32_t STAGE_BYTES = (OFF_RET + RET_BYTES + 127u) & ~127u;
-  static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES]
+  static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES], tile id of each stage
+  static_assert(24 * TMA_STAGES <= 128, "barriers and tile ids must fit BAR_BYTES");
   static constexpr uint32_t SMEM_BYTES = 128 + BAR_BYTES + TMA_STAGES * STAGE_BYTES;
 };
 
@@ -495,6 +498,8 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t full0 = smem_base, empty0 = smem_base + 8 * TMA_STAGES;
+  volatile uint64_t* tile_slot =
+      reinterpret_cast<volatile uint64_t*>(smem_raw + (smem_base + 16 * TMA_STAGES - tma::smem_u32(smem_raw)));
   const uint32_t data0 = smem_base + L::BAR_BYTES;
   const uint64_t n_tiles = p.n / TMA_TILE;
   const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
@@ -518,14 +523,22 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 
   if (warp == TMA_CONSUMER_WARPS) {
     // ---------------- producer ----------------
+    // Tiles are handed out by a global ticket counter (first come, first served), so CTAs that run faster
+    // take more tiles and the launch ends with every CTA busy until the tickets run out.  Launch L owns the
+    // tickets [work_base, work_base + n_tiles + gridDim.x): each CTA draws exactly one ticket past the end.
     if (lane == 0) {
       const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
       const uint32_t tx = SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u);
-      uint32_t it = 0;
-      for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t it = 0;; ++it) {
         const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
         tma::mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);  // first round passes at once
+        const uint64_t tile = atomicAdd(p.work_counter, 1ull) - p.work_base;
         const uint32_t bar = full0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
+        tile_slot[s] = tile;
+        if (tile >= n_tiles) {  // out of work: tell the consumers and stop
+          tma::mbar_arrive(bar);
+          break;
+        }
         const uint64_t e0 = p.first + tile * TMA_TILE;
         tma::mbar_expect_tx(bar, tx);
 #pragma unroll
@@ -542,11 +555,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   } else {
     // ---------------- consumers ----------------
     const uint32_t tid = threadIdx.x;  // 0..255
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
       const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
-      const uint64_t base = p.first + tile * TMA_TILE + tid * V;
       tma::mbar_wait(full0 + 8 * s, parity);
+      const uint64_t tile = tile_slot[s];
+      if (tile >= n_tiles) break;
+      const uint64_t base = p.first + tile * TMA_TILE + tid * V;
 
       Group<KIND, V> g;
       act_t action[V];
