@@ -46,7 +46,7 @@ struct mgym_env {
   float* h_obs = nullptr;
   float* h_reward = nullptr;
   uint8_t* h_flags = nullptr;
-  unsigned long long* work = nullptr;   // 3 ticket counters: caller's stream, pipe stream 0, pipe stream 1
+  unsigned long long* work = nullptr;   // ticket counters: step on the caller's stream, pipe streams 0 and 1, rollout
   uint64_t work_issued[3] = {0, 0, 0};  // tickets handed to launches so far, per counter
   int work_slot = 0;                    // counter the next TMA launch uses
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
@@ -525,8 +525,8 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
     }
     MGYM_CUDA(cudaMalloc(&e->stats, 5 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMemset(e->stats, 0, 5 * sizeof(unsigned long long)));
-    MGYM_CUDA(cudaMalloc(&e->work, 3 * sizeof(unsigned long long)));
-    MGYM_CUDA(cudaMemset(e->work, 0, 3 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMalloc(&e->work, 4 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMemset(e->work, 0, 4 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMalloc(&e->bad_action, sizeof(uint32_t)));
     MGYM_CUDA(cudaMemset(e->bad_action, 0, sizeof(uint32_t)));
     MGYM_CUDA(cudaDeviceSynchronize());
@@ -802,6 +802,10 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   if (done_count_out) MGYM_CUDA(cudaMemsetAsync(done_count_out, 0, sizeof(unsigned long long), st));
   const bool vec4 = e->vec4 && aligned16(actions) && aligned16(obs_traj) && aligned16(reward_traj) &&
                     aligned16(flags_traj);
+  // warp-tile tickets of this launch start at 0: the rollout has its own counter, cleared in-stream
+  p.work_counter = e->work + 3;
+  p.work_base = 0;
+  MGYM_CUDA(cudaMemsetAsync(e->work + 3, 0, sizeof(unsigned long long), st));
   int rc = dispatch<true>(e, p, vec4, st);
   if (rc != MGYM_OK) return rc;
   e->t += K;

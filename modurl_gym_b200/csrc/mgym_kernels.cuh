@@ -204,8 +204,8 @@ struct Group {
   uint32_t flags[V];
 };
 
-template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true>
-__device__ __forceinline__ void step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
+template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true, bool DEFER_RESET = false>
+__device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
                                            const typename Env<KIND>::act_t (&action)[V], bool track_ret,
                                            Group<KIND, V>& g, StatAcc& acc) {
   using E = Env<KIND>;
@@ -266,6 +266,16 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
       }
     }
   }
+  if constexpr (AUTO && DEFER_RESET) {
+    // The caller hands the finished envs to the reset warp; only what needs no random draw is done here.
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const bool hit = (pending >> v) & 1u;
+      g.steps[v] = hit ? 0u : g.steps[v];
+      g.ret[v] = hit ? 0.0f : g.ret[v];
+    }
+    return pending;
+  }
   if constexpr (AUTO) {
     while (pending) {
       const int sel = __ffs(pending) - 1;
@@ -277,7 +287,7 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
 #pragma unroll
         for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
       } else {
-                E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
+        E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
       }
       if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
 #pragma unroll
@@ -294,6 +304,7 @@ __device__ __forceinline__ void step_group(const KernelParams& p, bool count, ui
       }
     }
   }
+  return 0u;
 }
 
 template <int MODE>
@@ -463,7 +474,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 constexpr int TMA_STAGES = MGYM_TMA_STAGES;
 constexpr int TMA_CONSUMER_WARPS = 8;
-constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 1) * 32;  // + one producer warp
+constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 2) * 32;  // + one producer warp + one reset warp
+constexpr int TMA_RESET_BUFFERS = 2;                         // request queues in flight
 constexpr int TMA_TILE = TMA_CONSUMER_WARPS * 32 * 4;       // envs per CTA tile: 256 consumer threads x V=4
 
 template <int KIND, int CNT>
@@ -479,13 +491,25 @@ struct TmaLayout {
   static constexpr uint32_t STAGE_BYTES = (OFF_RET + RET_BYTES + 127u) & ~127u;
   static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES], tile id of each stage
   static_assert(24 * TMA_STAGES <= 128, "barriers and tile ids must fit BAR_BYTES");
-  static constexpr uint32_t SMEM_BYTES = 128 + BAR_BYTES + TMA_STAGES * STAGE_BYTES;
+  // reset queues: per buffer {q_full, q_empty mbarriers, tile id, count} (32 B) + TMA_TILE uint16 env indices
+  static constexpr uint32_t QUEUE_BYTES = TMA_RESET_BUFFERS * (32 + TMA_TILE * 2);
+  static constexpr uint32_t OFF_QUEUE = BAR_BYTES + TMA_STAGES * STAGE_BYTES;
+  static constexpr uint32_t SMEM_BYTES = 128 + OFF_QUEUE + QUEUE_BYTES;
 };
 
-// Warp-specialised: warp 8 is the TMA producer (one elected lane arms full[s] and launches the six
-// bulk copies of a 1024-env tile once the consumers have released stage s through empty[s]); warps
-// 0-7 are consumers (wait full[s], pull their 4 envs out of shared memory, release the stage, step,
-// store straight from registers).
+// Warp-specialised: warp 8 is the TMA producer (one elected lane draws a tile ticket, arms full[s] and
+// launches the six bulk copies of a 1024-env tile once the consumers have released stage s through
+// empty[s]); warps 0-7 are consumers (wait full[s], pull their 4 envs out of shared memory, release the
+// stage, step, store straight from registers); warp 9 is the reset warp.
+//
+// Reset warp.  A finished env needs a Philox block and four f64->f32 uniforms (~130 instructions), but only
+// 4-6 lanes of a consumer warp have one per step, so done in place that costs every consumer warp a whole
+// pass: ~25 % of all issued instructions, and under the 1 kW power cap the step is issue-bound.  Instead the
+// consumers only APPEND the finished env's index to a shared-memory queue (and clear its counter), store the
+// tile, and arrive on q_full[b] -- whose release orders their stores before whatever the reset warp does
+// next.  The reset warp then draws the new states with all 32 lanes busy (46 per tile on average = 2
+// passes per 1024 envs instead of 10) and patches them into the state rows (and obs_out) in global memory.
+// Consumers never wait for it except to reuse a queue buffer two tiles later.
 template <int KIND, int CNT>
 __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_tma(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
@@ -500,6 +524,13 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   const uint32_t full0 = smem_base, empty0 = smem_base + 8 * TMA_STAGES;
   volatile uint64_t* tile_slot =
       reinterpret_cast<volatile uint64_t*>(smem_raw + (smem_base + 16 * TMA_STAGES - tma::smem_u32(smem_raw)));
+  // reset queues, one per buffer: [q_full mbarrier][q_empty mbarrier][tile id u64][count u32, pad][uint16 x TMA_TILE]
+  constexpr uint32_t QSTRIDE = 32 + TMA_TILE * 2;
+  const uint32_t queue0 = smem_base + L::OFF_QUEUE;
+  uint8_t* const queue_ptr = smem_raw + (queue0 - tma::smem_u32(smem_raw));
+  auto q_tile = [&](uint32_t b) { return reinterpret_cast<volatile uint64_t*>(queue_ptr + b * QSTRIDE + 16); };
+  auto q_count = [&](uint32_t b) { return reinterpret_cast<uint32_t*>(queue_ptr + b * QSTRIDE + 24); };
+  auto q_items = [&](uint32_t b) { return reinterpret_cast<uint16_t*>(queue_ptr + b * QSTRIDE + 32); };
   const uint32_t data0 = smem_base + L::BAR_BYTES;
   const uint64_t n_tiles = p.n / TMA_TILE;
   const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
@@ -511,6 +542,11 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     for (int s = 0; s < TMA_STAGES; ++s) {
       tma::mbar_init(full0 + 8 * s, 1);
       tma::mbar_init(empty0 + 8 * s, TMA_CONSUMER_WARPS);
+    }
+    for (int b = 0; b < TMA_RESET_BUFFERS; ++b) {
+      tma::mbar_init(queue0 + b * QSTRIDE, TMA_CONSUMER_WARPS);  // q_full: every consumer warp has stored its tile
+      tma::mbar_init(queue0 + b * QSTRIDE + 8, 1);               // q_empty: the reset warp is done with the buffer
+      *q_count(b) = 0u;
     }
     tma::fence_mbar_init();
   }
@@ -552,6 +588,44 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       }
     }
     __syncwarp();
+  } else if (warp == TMA_CONSUMER_WARPS + 1) {
+    // ---------------- reset warp ----------------
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t qb = it % TMA_RESET_BUFFERS, qround = it / TMA_RESET_BUFFERS;
+      const uint32_t q_full = queue0 + qb * QSTRIDE, q_empty = q_full + 8;
+      tma::mbar_wait(q_full, qround & 1u);  // acquire: every consumer warp's stores of this tile are visible
+      const uint64_t tile = *q_tile(qb);
+      if (tile >= n_tiles) break;
+      const uint32_t count = *q_count(qb);
+      const uint16_t* items = q_items(qb);
+      const uint64_t tile_base = p.first + tile * TMA_TILE;
+      for (uint32_t j = lane; j < count; j += 32) {
+        const uint64_t local = tile_base + items[j];
+        const uint64_t gid = p.env_base + local;
+        float ns[SD];
+        if (p.reset_pool) {
+          const uint64_t k = (gid + p.t) % p.pool_len;
+#pragma unroll
+          for (int c = 0; c < SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + k];
+        } else {
+          E::reset(philox_env(p.seed, gid, p.t, TAG_AUTO_RESET), ns);
+        }
+#pragma unroll
+        for (int c = 0; c < SD; ++c) p.state[(uint64_t)c * p.ld + local] = ns[c];
+        if (p.obs_out) {  // the observation the caller sees is the post-reset one
+          float no[OD];
+          E::obs(ns, no);
+#pragma unroll
+          for (int c = 0; c < OD; ++c) p.obs_out[(uint64_t)c * p.ld + local] = no[c];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        *q_count(qb) = 0u;
+        tma::mbar_arrive(q_empty);
+      }
+    }
+    __syncwarp();
   } else {
     // ---------------- consumers ----------------
     const uint32_t tid = threadIdx.x;  // 0..255
@@ -559,7 +633,15 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       const uint32_t s = it % TMA_STAGES, parity = (it / TMA_STAGES) & 1u;
       tma::mbar_wait(full0 + 8 * s, parity);
       const uint64_t tile = tile_slot[s];
-      if (tile >= n_tiles) break;
+      const uint32_t qb = it % TMA_RESET_BUFFERS, qround = it / TMA_RESET_BUFFERS;
+      const uint32_t q_full = queue0 + qb * QSTRIDE, q_empty = q_full + 8;
+      tma::mbar_wait(q_empty, (qround & 1u) ^ 1u);  // the reset warp has finished this buffer's previous tile
+      if (tid == 0) *q_tile(qb) = tile;              // also carries the end-of-work sentinel
+      if (tile >= n_tiles) {
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(q_full);
+        break;
+      }
       const uint64_t base = p.first + tile * TMA_TILE + tid * V;
 
       Group<KIND, V> g;
@@ -602,12 +684,21 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         g.flags[v] = g.steps[v] & 1u;
         g.steps[v] += 1;
       }
+      uint32_t pending = 0;
 #else
+      uint32_t pending;
       if (want_final)
-        step_group<KIND, V, true, true>(p, true, base, p.t, action, track_ret, g, acc);
+        pending = step_group<KIND, V, true, true, true, true>(p, true, base, p.t, action, track_ret, g, acc);
       else
-        step_group<KIND, V, true, false>(p, true, base, p.t, action, track_ret, g, acc);
+        pending = step_group<KIND, V, true, false, true, true>(p, true, base, p.t, action, track_ret, g, acc);
 #endif
+      if (pending) {  // append this lane's finished envs (their index inside the tile) to the reset queue
+        uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc(pending));
+        uint16_t* items = q_items(qb);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if ((pending >> v) & 1u) items[pos++] = (uint16_t)(tid * V + v);
+      }
 
 #pragma unroll
       for (int c = 0; c < SD; ++c) {
@@ -660,6 +751,8 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
         stv<uint8_t, V>(p.flags_out + base, fl);
       }
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(q_full);
     }
   }
   stats_flush<KIND>(acc, p);
@@ -683,8 +776,14 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
   const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
   const uint32_t lane = threadIdx.x & 31;
 
-  // warp-uniform trip count so every lane reaches the ballots
-  for (uint64_t grp0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); grp0 < groups; grp0 += stride) {
+  // Warp tiles (32 lanes x V envs) are handed out by the global ticket counter, like the tiles of the step
+  // kernel: faster warps take more, and the trip count stays warp-uniform so every lane reaches the ballots.
+  for (;;) {
+    unsigned long long ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.work_counter, 1ull) - p.work_base;
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const uint64_t grp0 = ticket * 32;
+    if (grp0 >= groups) break;
     const uint64_t grp = grp0 + lane;
     const bool active = grp < groups;
     const uint64_t base = p.first + (active ? grp * V : 0);
