@@ -284,12 +284,19 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
       return dispatch_mode<KIND, 4, false>(e, tail, st);
     }
   }
+  // rollout_kernel's FULL form: complete warp tiles, all three trajectory outputs, no action validation
+  [[maybe_unused]] const bool full = ROLLOUT && V == 4 && autor && p.n % (32 * V) == 0 && p.obs_out && p.reward_out &&
+                                     p.flags_out && !p.bad_action;
 #define MGYM_LAUNCH(AUTO_, CNT_)                                                                         \
   do {                                                                                                   \
-    if constexpr (ROLLOUT)                                                                               \
-      return launch_persistent(rollout_kernel<KIND, V, AUTO_, CNT_>, e, p, groups, st);                  \
-    else                                                                                                 \
+    if constexpr (ROLLOUT) {                                                                             \
+      if constexpr (AUTO_ && V == 4) {                                                                   \
+        if (full) return launch_persistent(rollout_kernel<KIND, V, AUTO_, CNT_, true>, e, p, groups, st); \
+      }                                                                                                  \
+      return launch_persistent(rollout_kernel<KIND, V, AUTO_, CNT_, false>, e, p, groups, st);           \
+    } else {                                                                                             \
       return launch_persistent(step_kernel<KIND, V, AUTO_, CNT_>, e, p, groups, st);                     \
+    }                                                                                                    \
   } while (0)
   if (!autor) MGYM_LAUNCH(false, CNT_U32);
   if constexpr (KIND == 0) {

@@ -12,6 +12,8 @@
 // set of atomics per CTA.  The per-env work is shared: step_group().
 #pragma once
 
+#include <type_traits>
+
 #include "mgym_device.cuh"
 
 #ifndef MGYM_MIN_BLOCKS
@@ -27,7 +29,23 @@
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
 
+#ifndef MGYM_ACT_PF_DIST
+#define MGYM_ACT_PF_DIST 4
+#endif
+#ifndef MGYM_ACT_PF_LEVEL
+#define MGYM_ACT_PF_LEVEL 1
+#endif
+
 namespace mgym {
+
+template <int LEVEL>
+__device__ __forceinline__ void prefetch_global(const void* ptr) {
+  if constexpr (LEVEL == 1) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+  } else {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+  }
+}
 
 enum CounterMode : int { CNT_NONE = 0, CNT_U16 = 1, CNT_U32 = 2 };
 
@@ -204,7 +222,92 @@ struct Group {
   uint32_t flags[V];
 };
 
-template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true, bool DEFER_RESET = false>
+// What step_group does with the envs that finished (AUTO only):
+//   RESET_IN_PLACE  tallies them and draws their reset states right away (per-call step, LDG form)
+//   RESET_DEFERRED  tallies them, clears their counters and returns their slot mask: the TMA step kernel
+//                   hands them to its reset warp
+//   RESET_BY_CALLER neither tallies nor resets: the rollout kernel does both behind ONE warp vote, so a
+//                   step in which no env of the warp finished pays nothing for statistics or resets
+enum ResetMode : int { RESET_IN_PLACE = 0, RESET_DEFERRED = 1, RESET_BY_CALLER = 2 };
+
+// Draws the reset states of the slots in `pending` (bit v = slot v), one slot per lane per pass.
+template <int KIND, int V>
+__device__ __forceinline__ void reset_pending(const KernelParams& p, uint64_t base, uint64_t t, uint32_t pending,
+                                              Group<KIND, V>& g) {
+  using E = Env<KIND>;
+  while (pending) {
+    const int sel = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const uint64_t gid = p.env_base + base + sel;
+    float ns[E::SD], no[E::OD];
+    if (p.reset_pool) {
+      const uint64_t j = (gid + t) % p.pool_len;
+#pragma unroll
+      for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
+    } else {
+      E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
+    }
+    if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const bool hit = v == sel;
+#pragma unroll
+      for (int c = 0; c < E::SD; ++c) g.st[v][c] = hit ? ns[c] : g.st[v][c];
+      if constexpr (!E::OBS_IS_STATE) {
+#pragma unroll
+        for (int c = 0; c < E::OD; ++c) g.obs[v][c] = hit ? no[c] : g.obs[v][c];
+      }
+      g.steps[v] = hit ? 0u : g.steps[v];
+      g.ret[v] = hit ? 0.0f : g.ret[v];
+    }
+  }
+}
+
+// The flags of a group packed one byte per slot (what the flags store writes for V = 4).
+template <int KIND, int V>
+__device__ __forceinline__ uint32_t packed_flags(const Group<KIND, V>& g) {
+  static_assert(V <= 4, "one byte per slot");
+  uint32_t w = 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v) w |= g.flags[v] << (8 * v);
+  return w;
+}
+
+// Episode statistics of the finished slots from the packed flags: three population counts per group instead
+// of three selects and adds per env.  Must run BEFORE reset_pending (it reads the finishing counters / returns).
+template <int KIND, int V, bool TALLY_LEN>
+__device__ __forceinline__ void tally_packed(uint32_t w, const Group<KIND, V>& g, StatAcc& acc) {
+  using E = Env<KIND>;
+  acc.episodes += __popc((w | (w >> 1)) & 0x01010101u);
+  acc.terminated += __popc(w & 0x01010101u);
+  acc.truncated += __popc(w & 0x02020202u);
+  if constexpr (TALLY_LEN || !E::ANALYTIC_RETURN) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const bool hit = ((w >> (8 * v)) & 0xffu) != 0;
+      if constexpr (TALLY_LEN) acc.length_sum += hit ? g.steps[v] : 0u;
+      if constexpr (!E::ANALYTIC_RETURN) {
+        if (hit) acc.return_sum += (double)g.ret[v];
+      }
+    }
+  }
+}
+
+// Do all V slots satisfy the kind's entry invariant (always true for kinds without one)?
+template <int KIND, int V>
+__device__ __forceinline__ bool group_trusted(const Group<KIND, V>& g) {
+  bool mine = true;
+  if constexpr (Env<KIND>::HAS_TRUSTED) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) mine = mine && Env<KIND>::trusted_entry(g.st[v]);
+  }
+  return mine;
+}
+
+// TRUSTED (kinds with Env::HAS_TRUSTED): the caller has established Env::trusted_entry for every slot, which the
+// dynamics themselves then preserve, so the fast form runs without its per-step precondition test.
+template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true, int RESET = RESET_IN_PLACE,
+          bool TRUSTED = false>
 __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
                                            const typename Env<KIND>::act_t (&action)[V], bool track_ret,
                                            Group<KIND, V>& g, StatAcc& acc) {
@@ -212,7 +315,14 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
   float aux[V];
   bool ok[V];
   bool all_ok = true;
-  if constexpr (E::HAS_BATCH) {
+  if constexpr (TRUSTED && E::HAS_TRUSTED) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      aux[v] = 0.0f;
+      ok[v] = true;
+      E::dynamics_trusted(g.st[v], action[v], p.k);
+    }
+  } else if constexpr (E::HAS_BATCH) {
 #pragma unroll
     for (int v = 0; v < V; ++v) aux[v] = 0.0f;
     E::template dynamics_fast_batch<V>(g.st, action, p.k, ok);
@@ -251,7 +361,7 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
         for (int c = 0; c < E::OD; ++c) g.fin[v][c] = g.obs[v][c];
       }
     }
-    if constexpr (AUTO) {
+    if constexpr (AUTO && RESET != RESET_BY_CALLER) {
       const bool done = g.flags[v] != 0;
       pending |= done ? (1u << v) : 0u;
       // flags are 0 for a live env, so the masks need no extra select
@@ -266,7 +376,7 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
       }
     }
   }
-  if constexpr (AUTO && DEFER_RESET) {
+  if constexpr (AUTO && RESET == RESET_DEFERRED) {
     // The caller hands the finished envs to the reset warp; only what needs no random draw is done here.
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -276,34 +386,7 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
     }
     return pending;
   }
-  if constexpr (AUTO) {
-    while (pending) {
-      const int sel = __ffs(pending) - 1;
-      pending &= pending - 1;
-      const uint64_t gid = p.env_base + base + sel;
-      float ns[E::SD], no[E::OD];
-      if (p.reset_pool) {
-        const uint64_t j = (gid + t) % p.pool_len;
-#pragma unroll
-        for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
-      } else {
-        E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
-      }
-      if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const bool hit = v == sel;
-#pragma unroll
-        for (int c = 0; c < E::SD; ++c) g.st[v][c] = hit ? ns[c] : g.st[v][c];
-        if constexpr (!E::OBS_IS_STATE) {
-#pragma unroll
-          for (int c = 0; c < E::OD; ++c) g.obs[v][c] = hit ? no[c] : g.obs[v][c];
-        }
-        g.steps[v] = hit ? 0u : g.steps[v];
-        g.ret[v] = hit ? 0.0f : g.ret[v];
-      }
-    }
-  }
+  if constexpr (AUTO && RESET == RESET_IN_PLACE) reset_pending<KIND, V>(p, base, t, pending, g);
   return 0u;
 }
 
@@ -328,7 +411,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
   StatAcc acc;
   const uint64_t groups = p.n / V;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const bool track_ret = p.ep_return != nullptr;
+  const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
   const bool want_final = p.final_obs_out != nullptr;
 
   for (uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; grp < groups; grp += stride) {
@@ -688,9 +771,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 #else
       uint32_t pending;
       if (want_final)
-        pending = step_group<KIND, V, true, true, true, true>(p, true, base, p.t, action, track_ret, g, acc);
+        pending = step_group<KIND, V, true, true, true, RESET_DEFERRED>(p, true, base, p.t, action, track_ret, g, acc);
       else
-        pending = step_group<KIND, V, true, false, true, true>(p, true, base, p.t, action, track_ret, g, acc);
+        pending = step_group<KIND, V, true, false, true, RESET_DEFERRED>(p, true, base, p.t, action, track_ret, g, acc);
 #endif
       if (pending) {  // append this lane's finished envs (their index inside the tile) to the reset queue
         uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc(pending));
@@ -761,23 +844,28 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 // =============================================================================================
 // Mode 2: fused K-step rollout kernel
 // =============================================================================================
-template <int KIND, int V, bool AUTO, int CNT>
+// FULL (chosen by the host): every warp tile is complete (n % (32 V) == 0), all three trajectory outputs are
+// present and action validation is off -- the loop then carries no per-lane `active` predicate and no null
+// tests.  Per step, everything that concerns finished envs (statistics, done count, Philox resets) sits behind
+// ONE warp vote on the packed flags word: a warp tile in which nothing finished (MountainCar: almost always)
+// pays one compare and one VOTE for it.
+template <int KIND, int V, bool AUTO, int CNT, bool FULL>
 __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD;
+  static_assert(!FULL || (AUTO && V == 4), "the FULL form is built for the vector auto-reset path only");
   StatAcc acc;
-  uint32_t warp_dones = 0;  // identical in every lane of the warp (ballot + popc)
+  uint32_t dones = 0;  // finished env-steps of this lane's groups
   const uint64_t groups = p.n / V;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const bool track_ret = p.ep_return != nullptr;
+  const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
   const bool policy = p.actions == nullptr;
   const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
   const uint32_t lane = threadIdx.x & 31;
 
   // Warp tiles (32 lanes x V envs) are handed out by the global ticket counter, like the tiles of the step
-  // kernel: faster warps take more, and the trip count stays warp-uniform so every lane reaches the ballots.
+  // kernel: faster warps take more, and the trip count stays warp-uniform so every lane reaches the votes.
   for (;;) {
     unsigned long long ticket = 0;
     if (lane == 0) ticket = atomicAdd(p.work_counter, 1ull) - p.work_base;
@@ -785,7 +873,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
     const uint64_t grp0 = ticket * 32;
     if (grp0 >= groups) break;
     const uint64_t grp = grp0 + lane;
-    const bool active = grp < groups;
+    const bool active = FULL || grp < groups;
     const uint64_t base = p.first + (active ? grp * V : 0);
     Group<KIND, V> g;
 #pragma unroll
@@ -820,9 +908,13 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
       }
     }
 
-    RawActions<act_t, V> a_next;
-    a_next.zero();
-    if (!policy && active) a_next.load(actions + base);
+    // Actions ping-pong between two registers (sets): the row of step k+1 is loaded into the one that step k
+    // does not read, so the load stays in flight for a whole step and no loop-carried copy exists that the
+    // compiler could hoist next to the load (it did: 34 % of all stall samples sat on that one move).
+    RawActions<act_t, V> a0, a1;
+    a0.zero();
+    a1.zero();
+    if (!policy && active) a0.load(actions + base);
 
     // Sum of the lengths of the episodes an env finishes during this launch = steps_before + K - steps_after,
     // so the per-step tally is not needed here (counters saturate only after 4e9 steps).
@@ -835,19 +927,29 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
 
     // running output pointers: one 64-bit add per array per step instead of a multiply-add chain per store
     const uint64_t obs_step = (uint64_t)OD * p.ld;
-    float* obs_ptr = p.obs_out ? p.obs_out + base : nullptr;
-    float* rew_ptr = p.reward_out ? p.reward_out + base : nullptr;
-    uint8_t* flg_ptr = p.flags_out ? p.flags_out + base : nullptr;
+    float* obs_ptr = (FULL || p.obs_out) ? p.obs_out + base : nullptr;
+    float* rew_ptr = (FULL || p.reward_out) ? p.reward_out + base : nullptr;
+    uint8_t* flg_ptr = (FULL || p.flags_out) ? p.flags_out + base : nullptr;
     const act_t* act_ptr = actions ? actions + base + p.ld : nullptr;  // next step's row
 
-    for (uint32_t kk = 0; kk < p.K; ++kk) {
-      const uint64_t t = p.t + kk;
-      const RawActions<act_t, V> a_cur = a_next;
-      // prefetch the next step's actions first: the load stays in flight for the whole step
-      if (!policy && active && kk + 1 < p.K) {
-        a_next.load(act_ptr);
+    // One step of this warp tile.  `trusted_tag` selects the form without per-step precondition tests; the
+    // return value says whether the invariant behind it still holds (it can only break when a reset state
+    // comes from an injected pool, and is re-checked right there, under the same rare branch).
+    // loads the action row of step `row` (if there is one) and pulls the row MGYM_ACT_PF_DIST steps further
+    // towards the SM, so that the load itself hits L1/L2 rather than DRAM
+    auto load_row = [&](RawActions<act_t, V>& dst, uint32_t row) {
+      if (!policy && active && row < p.K) {
+#if MGYM_ACT_PF_DIST > 0
+        if (row + MGYM_ACT_PF_DIST < p.K) prefetch_global<MGYM_ACT_PF_LEVEL>(act_ptr + (uint64_t)MGYM_ACT_PF_DIST * p.ld);
+#endif
+        dst.load(act_ptr);
         act_ptr += p.ld;
       }
+    };
+    auto one_step = [&](auto trusted_tag, uint32_t kk, const RawActions<act_t, V>& a_cur) -> bool {
+      constexpr bool TRUSTED = decltype(trusted_tag)::value;
+      bool still = true;
+      const uint64_t t = p.t + kk;
       act_t action[V];
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
@@ -867,7 +969,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
 #pragma unroll
         for (int v = 0; v < V; ++v) action[v] = a_cur.get(v);
       }
-      if constexpr (!E::CONTINUOUS) {
+      if constexpr (!E::CONTINUOUS && !FULL) {
         if (p.bad_action) {
 #pragma unroll
           for (int v = 0; v < V; ++v)
@@ -875,36 +977,74 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
         }
       }
 
-      step_group<KIND, V, AUTO, false, !kLenIdentity>(p, active, base, t, action, track_ret, g, acc);
+      step_group<KIND, V, AUTO, false, false, RESET_BY_CALLER, TRUSTED>(p, active, base, t, action, track_ret, g, acc);
 
-#pragma unroll
-      for (int v = 0; v < V; ++v) warp_dones += __popc(__ballot_sync(0xffffffffu, active && g.flags[v] != 0));
+      // ---- trajectory stores (before the resets: reward and flags belong to the finishing step; the
+      // observation is stored after them, it is the post-reset one) ----
+      const uint32_t w = packed_flags<KIND, V>(g);
       if (active) {
-        if (obs_ptr) {
-#pragma unroll
-          for (int c = 0; c < OD; ++c) {
-            Vec<float, V> o;
-#pragma unroll
-            for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
-            stv<float, V>(obs_ptr + (uint64_t)c * p.ld, o);
-          }
-          obs_ptr += obs_step;
-        }
-        if (rew_ptr) {
+        if (FULL || rew_ptr) {
           Vec<float, V> rw;
 #pragma unroll
           for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
           stv<float, V>(rew_ptr, rw);
           rew_ptr += p.ld;
         }
-        if (flg_ptr) {
-          Vec<uint8_t, V> fl;
-#pragma unroll
-          for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
-          stv<uint8_t, V>(flg_ptr, fl);
+        if (FULL || flg_ptr) {
+          if constexpr (V == 4) {
+            *reinterpret_cast<uint32_t*>(flg_ptr) = w;
+          } else {
+            *flg_ptr = (uint8_t)w;
+          }
           flg_ptr += p.ld;
         }
       }
+
+      // ---- finished envs: one warp vote, then statistics + resets only where needed ----
+      const uint32_t wf = active ? w : 0u;
+      if (__ballot_sync(0xffffffffu, wf != 0u) != 0u) {
+        dones += __popc((wf | (wf >> 1)) & 0x01010101u);
+        if constexpr (AUTO) {
+          tally_packed<KIND, V, !kLenIdentity>(wf, g, acc);
+          uint32_t pending = 0;
+#pragma unroll
+          for (int v = 0; v < V; ++v) pending |= ((w >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
+          reset_pending<KIND, V>(p, base, t, pending, g);
+          if constexpr (TRUSTED && E::HAS_TRUSTED) {
+            if (p.reset_pool) still = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));
+          }
+        }
+      }
+
+      if (active && (FULL || obs_ptr)) {
+#pragma unroll
+        for (int c = 0; c < OD; ++c) {
+          Vec<float, V> o;
+#pragma unroll
+          for (int v = 0; v < V; ++v) o.v[v] = E::OBS_IS_STATE ? g.st[v][c < SD ? c : 0] : g.obs[v][c];
+          stv<float, V>(obs_ptr + (uint64_t)c * p.ld, o);
+        }
+        obs_ptr += obs_step;
+      }
+      return still;
+    };
+    bool trusted = false;  // warp-uniform
+    if constexpr (E::HAS_TRUSTED) trusted = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));  // zeros (inactive) pass
+    auto step_any = [&](uint32_t kk, const RawActions<act_t, V>& a_cur) {
+      if constexpr (E::HAS_TRUSTED) {
+        if (trusted) {
+          trusted = one_step(std::true_type{}, kk, a_cur);
+          return;
+        }
+      }
+      one_step(std::false_type{}, kk, a_cur);
+    };
+    for (uint32_t kk = 0; kk < p.K; kk += 2) {
+      load_row(a1, kk + 1);
+      step_any(kk, a0);
+      if (kk + 1 >= p.K) break;
+      load_row(a0, kk + 2);
+      step_any(kk + 1, a1);
     }
     if constexpr (kLenIdentity) {
       if (active) {
@@ -943,7 +1083,7 @@ __global__ void __launch_bounds__(256, MGYM_ROLLOUT_MIN_BLOCKS) rollout_kernel(c
       }
     }
   }
-  if (lane == 0) acc.done_steps = warp_dones;
+  acc.done_steps = dones;
   stats_flush<KIND>(acc, p);
 }
 

@@ -559,6 +559,68 @@ def test_fallback_paths_match_oracle(gym, oracle, kind, auto):
     env.close()
 
 
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("n", [2048, 515])
+def test_rollout_adversarial_states_match_oracle(gym, oracle, kind, n):
+    """The fused rollout from NaN / inf / huge injected states: its reference-form fallbacks, and for MountainCar the
+    entry test that decides between the trusted and the checked loop, give the oracle's results."""
+    K = 6
+    rng = np.random.default_rng(1700 + kind)
+    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=6)
+    ref = oracle.VecState(kind, n, auto_reset=1, seed=6)
+    env.reset(), ref.reset()
+    with np.errstate(all="ignore"):
+        for rep in range(2):
+            st = adversarial_states(kind, n, rng)
+            if rep == 1:  # whole warps of ordinary states next to whole warps of adversarial ones
+                st[:, : n // 2] = random_states(rng, kind, n // 2)
+            env.set_state(dev(st))
+            ref.state[:] = st
+            ref.steps[:] = 0
+            ref.ep_return[:] = 0
+            a = random_actions(rng, kind, (K, n))
+            out = env.rollout(K, dev(a))
+            o, r, f, dc = ref.rollout(K, a)
+            assert_bit_equal(host(out.flags), f, f"{KIND_NAMES[kind]} flags rep {rep}")
+            assert_equal_or_both_nan(host(out.obs), o, f"{KIND_NAMES[kind]} obs rep {rep}")
+            assert_equal_or_both_nan(host(out.reward), r, f"{KIND_NAMES[kind]} reward rep {rep}")
+            assert int(out.done_count.item()) == dc
+    env.close()
+
+
+def test_mountain_car_rollout_leaves_trusted_loop_on_bad_pool_state(gym, oracle):
+    """MountainCar's rollout runs without per-step precondition tests once its entry invariant holds; a reset
+    state injected through the pool can break the invariant, and the kernel must notice (it re-tests after pool
+    resets) and continue in the checked loop.  Short episodes (TimeLimit 3) make every env reset from a pool
+    that holds NaN, inf and huge positions next to ordinary ones."""
+    n, K = 4096, 24
+    rng = np.random.default_rng(77)
+    env = gym.GpuVecEnv(1, n, auto_reset=True, seed=9, max_episode_steps=3)
+    ref = oracle.VecState(1, n, auto_reset=1, seed=9, max_episode_steps=3)
+    pool = random_states(rng, 1, 257)
+    bad = adversarial_states(1, 257, rng)
+    pick = rng.random(257) < 0.1
+    pool[:, pick] = bad[:, pick]
+    env.set_reset_pool(dev(pool))
+    ref.set_reset_pool(pool)
+    env.reset(), ref.reset()
+    st = random_states(rng, 1, n)      # ordinary: every warp enters the trusted loop
+    env.set_state(dev(st))
+    ref.state[:] = st
+    ref.steps[:] = 0
+    with np.errstate(all="ignore"):
+        for chunk in range(2):
+            a = random_actions(rng, 1, (K, n))
+            out = env.rollout(K, dev(a))
+            o, r, f, dc = ref.rollout(K, a)
+            assert_bit_equal(host(out.flags), f, f"flags chunk {chunk}")
+            assert_equal_or_both_nan(host(out.obs), o, f"obs chunk {chunk}")
+            assert int(out.done_count.item()) == dc
+    s = env.stats()
+    assert (s.episodes, s.truncated, s.length_sum) == (ref.stats.episodes, ref.stats.truncated, ref.stats.length_sum)
+    env.close()
+
+
 def test_mountain_car_1000_step_chunked_rollout(gym, oracle):
     """BASELINE configs[2]: a 1000-step MountainCar rollout run as 32-step launches over one reused ring equals
     the oracle's single 1000-step rollout (flags, rewards, observations of every step, final state)."""
