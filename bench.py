@@ -297,6 +297,9 @@ def run_native(args, rank, local_rank, world):
             "e2e": {"value": float(n) * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                     "path": "mgym_step_host: pinned host actions -> device, step, obs/reward/flags -> pinned host",
+                    # what bounds it: bytes over each GPU's PCIe link per second of the timed region
+                    "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                    "bound": "pcie (22 B per env-step cross the link; the kernel itself takes 2 % of the call)",
                     "host_affinity_rank0": numa},
             "gpu_launches": args.steps,
             "clocks": clocks,
