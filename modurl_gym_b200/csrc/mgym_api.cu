@@ -167,6 +167,7 @@ KernelParams base_params(const mgym_env* e) {
   p.first = 0;
   p.ld = e->n;
   p.seed = e->seed;
+  p.keys = philox_keys(e->seed);
   p.env_base = e->cfg.env_index_base;
   p.t = e->t;
   p.k = e->k;

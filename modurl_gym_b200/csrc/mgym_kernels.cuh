@@ -75,6 +75,7 @@ struct KernelParams {
   uint64_t ld;     // row stride of every SoA buffer = envs in the handle
   uint64_t seed, env_base, t;
   uint32_t K;
+  PhiloxKeys keys;  // round keys of `seed`
   EnvConsts k;
 };
 
@@ -245,7 +246,7 @@ __device__ __forceinline__ void reset_pending(const KernelParams& p, uint64_t ba
 #pragma unroll
       for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
     } else {
-      E::reset(philox_env(p.seed, gid, t, TAG_AUTO_RESET), ns);
+      E::reset(philox_env(p.keys, gid, t, TAG_AUTO_RESET), ns);
     }
     if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
 #pragma unroll
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 #pragma unroll
           for (int c = 0; c < SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + k];
         } else {
-          E::reset(philox_env(p.seed, gid, p.t, TAG_AUTO_RESET), ns);
+          E::reset(philox_env(p.keys, gid, p.t, TAG_AUTO_RESET), ns);
         }
 #pragma unroll
         for (int c = 0; c < SD; ++c) p.state[(uint64_t)c * p.ld + local] = ns[c];
@@ -961,14 +962,14 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
         if constexpr (V == 4) {
-          const uint4 w = philox_env(p.seed, (p.env_base + base) >> 2, t, TAG_ACTION);
+          const uint4 w = philox_env(p.keys, (p.env_base + base) >> 2, t, TAG_ACTION);
           action[0] = action_from_word<KIND>(w.x);
           action[1] = action_from_word<KIND>(w.y);
           action[2] = action_from_word<KIND>(w.z);
           action[3] = action_from_word<KIND>(w.w);
         } else {
           const uint64_t gid = p.env_base + base;
-          const uint4 w = philox_env(p.seed, gid >> 2, t, TAG_ACTION);
+          const uint4 w = philox_env(p.keys, gid >> 2, t, TAG_ACTION);
           const uint32_t lane_word = (gid & 2) ? ((gid & 1) ? w.w : w.z) : ((gid & 1) ? w.y : w.x);
           action[0] = action_from_word<KIND>(lane_word);
         }
