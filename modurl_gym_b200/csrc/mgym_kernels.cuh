@@ -307,8 +307,9 @@ __device__ __forceinline__ bool group_trusted(const Group<KIND, V>& g) {
 
 // TRUSTED (kinds with Env::HAS_TRUSTED): the caller has established Env::trusted_entry for every slot, which the
 // dynamics themselves then preserve, so the fast form runs without its per-step precondition test.
+// OBS_VALID (kinds with Env::HAS_OBS_CACHE): g.obs is the observation of the state in g.st on entry.
 template <int KIND, int V, bool AUTO, bool WANT_FINAL, bool TALLY_LEN = true, int RESET = RESET_IN_PLACE,
-          bool TRUSTED = false>
+          bool TRUSTED = false, bool OBS_VALID = false>
 __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count, uint64_t base, uint64_t t,
                                            const typename Env<KIND>::act_t (&action)[V], bool track_ret,
                                            Group<KIND, V>& g, StatAcc& acc) {
@@ -340,7 +341,11 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       aux[v] = 0.0f;
-      ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
+      if constexpr (OBS_VALID && E::HAS_OBS_CACHE) {
+        ok[v] = E::dynamics_fast_cached(g.st[v], action[v], p.k, aux[v], g.obs[v]);
+      } else {
+        ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
+      }
       all_ok = all_ok && ok[v];
     }
   }
@@ -919,6 +924,10 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     // Actions ping-pong between two registers (sets): the row of step k+1 is loaded into the one that step k
     // does not read, so the load stays in flight for a whole step and no loop-carried copy exists that the
     // compiler could hoist next to the load (it did: 34 % of all stall samples sat on that one move).
+    if constexpr (E::HAS_OBS_CACHE) {  // step_group<OBS_VALID> relies on g.obs from here on
+#pragma unroll
+      for (int v = 0; v < V; ++v) E::obs(g.st[v], g.obs[v]);
+    }
     RawActions<act_t, V> a0, a1;
     a0.zero();
     a1.zero();
@@ -985,7 +994,8 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
         }
       }
 
-      step_group<KIND, V, AUTO, false, false, RESET_BY_CALLER, TRUSTED>(p, active, base, t, action, track_ret, g, acc);
+      step_group<KIND, V, AUTO, false, false, RESET_BY_CALLER, TRUSTED, true>(p, active, base, t, action, track_ret, g,
+                                                                              acc);
 
       // ---- trajectory stores (before the resets: reward and flags belong to the finishing step; the
       // observation is stored after them, it is the post-reset one) ----
