@@ -358,10 +358,15 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     if constexpr (AUTO) g.sbt[v] = SBT_NONE;  // auto-reset presumes reset() precedes every episode
-    g.flags[v] = E::outcome(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
+    if constexpr (E::OUTCOME_FROM_OBS) {
+      E::obs(g.st[v], g.obs[v]);
+      g.flags[v] = E::outcome_obs(g.st[v], g.obs[v], g.steps[v], p.k, g.reward[v]);
+    } else {
+      g.flags[v] = E::outcome(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
+    }
     if (track_ret) g.ret[v] = fadd(g.ret[v], g.reward[v]);
     if constexpr (!E::OBS_IS_STATE || WANT_FINAL) {
-      E::obs(g.st[v], g.obs[v]);
+      if constexpr (!E::OUTCOME_FROM_OBS) E::obs(g.st[v], g.obs[v]);
       if constexpr (WANT_FINAL) {
 #pragma unroll
         for (int c = 0; c < E::OD; ++c) g.fin[v][c] = g.obs[v][c];
