@@ -207,7 +207,19 @@ def run_native(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner (and, with NCCL_DEBUG=INFO, its topology log) on stdout when the
+        # communicator comes up; stdout is reserved for the ONE JSON line, so fd 1 points at stderr meanwhile.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()  # eager communicator creation
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from modurl_gym_b200.distributed import max_over_ranks, shard_range
 
