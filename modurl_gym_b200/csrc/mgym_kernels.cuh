@@ -778,20 +778,28 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         g.flags[v] = g.steps[v] & 1u;
         g.steps[v] += 1;
       }
-      uint32_t pending = 0;
 #else
-      uint32_t pending;
       if (want_final)
-        pending = step_group<KIND, V, true, true, true, RESET_DEFERRED>(p, true, base, p.t, action, track_ret, g, acc);
+        step_group<KIND, V, true, true, true, RESET_BY_CALLER>(p, true, base, p.t, action, track_ret, g, acc);
       else
-        pending = step_group<KIND, V, true, false, true, RESET_DEFERRED>(p, true, base, p.t, action, track_ret, g, acc);
+        step_group<KIND, V, true, false, true, RESET_BY_CALLER>(p, true, base, p.t, action, track_ret, g, acc);
 #endif
-      if (pending) {  // append this lane's finished envs (their index inside the tile) to the reset queue
-        uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc(pending));
+      // Everything about this lane's finished envs sits in one branch: statistics from the packed flags word,
+      // counters cleared, and their index inside the tile appended to the reset queue.
+      const uint32_t fw = packed_flags<KIND, V>(g);
+      const uint32_t fin = MGYM_EXP_MEMONLY ? 0u : fw;  // the memory-only experiment finishes nothing
+      if (fin) {
+        tally_packed<KIND, V, true>(fin, g, acc);
+        uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc((fin | (fin >> 1)) & 0x01010101u));
         uint16_t* items = q_items(qb);
 #pragma unroll
-        for (int v = 0; v < V; ++v)
-          if ((pending >> v) & 1u) items[pos++] = (uint16_t)(tid * V + v);
+        for (int v = 0; v < V; ++v) {
+          if ((fin >> (8 * v)) & 0xffu) {
+            items[pos++] = (uint16_t)(tid * V + v);
+            g.steps[v] = 0u;
+            g.ret[v] = 0.0f;
+          }
+        }
       }
 
 #pragma unroll
@@ -839,12 +847,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         for (int v = 0; v < V; ++v) rw.v[v] = g.reward[v];
         stv<float, V>(p.reward_out + base, rw);
       }
-      if (p.flags_out) {
-        Vec<uint8_t, V> fl;
-#pragma unroll
-        for (int v = 0; v < V; ++v) fl.v[v] = (uint8_t)g.flags[v];
-        stv<uint8_t, V>(p.flags_out + base, fl);
-      }
+      if (p.flags_out) *reinterpret_cast<uint32_t*>(p.flags_out + base) = fw;
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(q_full);
     }
