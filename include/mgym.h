@@ -158,7 +158,10 @@ int mgym_checkpoint_save(mgym_env *env, void *host_blob, size_t blob_bytes, void
 int mgym_checkpoint_load(mgym_env *env, const void *host_blob, size_t blob_bytes, void *stream);
 
 /* ---- the hot path ------------------------------------------------------------------ */
-/* One Gym::step for all N envs.  obs_out, reward_out, flags_out, final_obs_out may be NULL. */
+/* One Gym::step for all N envs.  obs_out, reward_out, flags_out, final_obs_out may be NULL.
+ * Not capturable into a CUDA graph (the step index that keys the Philox resets and the tile tickets are
+ * per-call launch parameters): on a capturing stream mgym_step / mgym_rollout return MGYM_ERR_BAD_ARGUMENT
+ * instead of recording a launch whose replay would be wrong.  Use mgym_rollout to fuse many steps. */
 int mgym_step(mgym_env *env, const void *actions, float *obs_out, float *reward_out, uint8_t *flags_out,
               float *final_obs_out, void *stream);
 /* K fused steps with state held in registers; only the trajectory is written.

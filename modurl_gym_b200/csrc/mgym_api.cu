@@ -340,6 +340,23 @@ int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* m
   return MGYM_OK;
 }
 
+// The step index (Philox counter) and the tile-ticket base are host-side launch parameters that change with
+// every call, so a captured launch replayed from a CUDA graph would repeat one step's random draws and find its
+// tickets spent.  Refuse capture instead of returning wrong results.
+int refuse_capture(cudaStream_t st, const char* what) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
+    cudaGetLastError();
+    return MGYM_OK;
+  }
+  if (status != cudaStreamCaptureStatusNone)
+    return fail(MGYM_ERR_BAD_ARGUMENT,
+                "%s: the stream is being captured into a CUDA graph; step index and tile tickets are per-call "
+                "launch parameters, a replay would be wrong (use mgym_rollout for fused multi-step launches)",
+                what);
+  return MGYM_OK;
+}
+
 bool is_host_pointer(const void* ptr) {
   cudaPointerAttributes attr{};
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
@@ -779,6 +796,7 @@ int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_ou
   e->work_slot = 0;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = refuse_capture(st, "mgym_step")) return rc;
   KernelParams p = base_params(e);
   p.actions = actions;
   // zero-copy observation: for kinds whose observation is the state, obs_out == state rows is a no-op
@@ -800,6 +818,7 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   if (K == 0) return MGYM_OK;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = refuse_capture(st, "mgym_rollout")) return rc;
   KernelParams p = base_params(e);
   p.actions = actions;
   p.obs_out = obs_traj;

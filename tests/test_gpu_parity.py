@@ -433,6 +433,27 @@ def test_invalid_action_is_reported(gym):
         env.step(torch.zeros((8, 1), dtype=torch.uint8, device="cuda"))  # wrong rank, cartpole.rs:392-403
 
 
+def test_stream_capture_is_refused(gym):
+    """A captured step would bake one step index and one ticket range into the graph; the ABI refuses instead."""
+    env = gym.GpuVecEnv(0, 4096, seed=1)
+    env.reset()
+    acts = env.sample_actions()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        graph.capture_begin()
+        try:
+            with pytest.raises(Exception, match="captured into a CUDA graph"):
+                env.step(acts)
+        finally:
+            graph.capture_end()
+    torch.cuda.synchronize()
+    info = env.step(acts)   # the handle is still usable afterwards
+    assert info.reward.shape == (4096,)
+    env.close()
+
+
 def test_reset_distribution_and_determinism(gym):
     """cartpole.rs:240: U[-0.05, 0.05); mountain_car.rs:281-283: U[-0.6,-0.4), v = 0; same seed => same stream
     (cartpole.rs:474-517), independent of how envs are split over handles."""
