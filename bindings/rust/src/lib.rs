@@ -56,6 +56,7 @@ impl Builder {
     pub fn auto_reset(mut self, v: bool) -> Self { self.cfg.auto_reset = v as i32; self }
     pub fn validate_actions(mut self, v: bool) -> Self { self.cfg.validate_actions = v as i32; self }
     pub fn env_index_base(mut self, v: u64) -> Self { self.cfg.env_index_base = v; self }
+    pub fn graph_capturable(mut self, v: bool) -> Self { self.cfg.device_clock = v as i32; self }
     pub fn build(self) -> Result<GpuVecEnv, MgymError> {
         let mut h = ptr::null_mut();
         check(unsafe { sys::mgym_create(self.kind as i32, self.num_envs, self.device, self.seed, &self.cfg, &mut h) })?;

@@ -19,6 +19,8 @@ pub struct mgym_config {
     pub track_stats: i32,
     pub validate_actions: i32,
     pub env_index_base: u64,
+    pub device_clock: i32, // 1 = CUDA-graph-capturable handle (step index + tile tickets on the device)
+    pub reserved0: i32,
 }
 
 #[repr(C)]

@@ -100,6 +100,12 @@ typedef struct mgym_config {
   int32_t track_stats;         /* default 1: episode count / length / return sums (auto_reset only) */
   int32_t validate_actions;    /* default 0: debug mode, see Errors above */
   uint64_t env_index_base;     /* global index of this handle's env 0 (multi-GPU slices) */
+  int32_t device_clock;        /* default 0.  1 = keep the step index and the tile-ticket base in device memory,
+                                  advanced by a one-thread kernel after every call: mgym_step, mgym_rollout and
+                                  mgym_sample_actions then carry no per-call launch parameter and may be captured
+                                  into a CUDA graph and replayed (same results as the eager calls).  Costs one
+                                  extra tiny launch per call; mgym_step_index then synchronises the device. */
+  int32_t reserved0;           /* 0 */
 } mgym_config;
 
 /* Episode statistics accumulated on the device since creation / mgym_stats_reset. */
@@ -159,9 +165,12 @@ int mgym_checkpoint_load(mgym_env *env, const void *host_blob, size_t blob_bytes
 
 /* ---- the hot path ------------------------------------------------------------------ */
 /* One Gym::step for all N envs.  obs_out, reward_out, flags_out, final_obs_out may be NULL.
- * Not capturable into a CUDA graph (the step index that keys the Philox resets and the tile tickets are
- * per-call launch parameters): on a capturing stream mgym_step / mgym_rollout return MGYM_ERR_BAD_ARGUMENT
- * instead of recording a launch whose replay would be wrong.  Use mgym_rollout to fuse many steps. */
+ * CUDA graphs: by default the step index that keys the Philox resets and the tile tickets are per-call launch
+ * parameters, so on a capturing stream mgym_step / mgym_rollout / mgym_sample_actions return
+ * MGYM_ERR_BAD_ARGUMENT instead of recording a launch whose replay would be wrong.  A handle created with
+ * cfg.device_clock = 1 keeps both on the device and IS capturable (launch-bound small batches: capture
+ * [policy, mgym_step] once, replay it per step).  mgym_reset, mgym_step_host and the state accessors are never
+ * capturable. */
 int mgym_step(mgym_env *env, const void *actions, float *obs_out, float *reward_out, uint8_t *flags_out,
               float *final_obs_out, void *stream);
 /* K fused steps with state held in registers; only the trajectory is written.

@@ -90,6 +90,8 @@ class GpuVecEnv {
     Builder& max_episode_steps(int v) { cfg_.max_episode_steps = v; return *this; }
     Builder& validate_actions(bool v) { cfg_.validate_actions = v; return *this; }
     Builder& env_index_base(uint64_t v) { cfg_.env_index_base = v; return *this; }
+    // step index and tile tickets on the device: step / rollout / sample_actions become CUDA-graph-capturable
+    Builder& graph_capturable(bool v) { cfg_.device_clock = v; return *this; }
     GpuVecEnv build() const { return GpuVecEnv(kind_, n_, device_, seed_, cfg_); }
 
    private:

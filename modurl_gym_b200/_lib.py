@@ -34,6 +34,8 @@ class Config(C.Structure):
         ("track_stats", C.c_int32),
         ("validate_actions", C.c_int32),
         ("env_index_base", C.c_uint64),
+        ("device_clock", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

@@ -49,6 +49,10 @@ struct mgym_env {
   unsigned long long* work = nullptr;   // ticket counters: step on the caller's stream, pipe streams 0 and 1, rollout
   uint64_t work_issued[3] = {0, 0, 0};  // tickets handed to launches so far, per counter
   int work_slot = 0;                    // counter the next TMA launch uses
+  // device clock (cfg.device_clock): {step index, first ticket of the step counter, finished CTAs of the
+  // running launch}; see KernelParams::t_dev / adv_clock
+  unsigned long long* clock = nullptr;
+  uint64_t call_tickets = 0;            // tickets the TMA launches of the running call draw from counter 0
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
 };
@@ -168,6 +172,8 @@ KernelParams base_params(const mgym_env* e) {
   p.ld = e->n;
   p.seed = e->seed;
   p.keys = philox_keys(e->seed);
+  p.t_dev = e->cfg.device_clock ? e->clock : nullptr;
+  p.base_dev = nullptr;  // set by launch_step_tma for counter 0
   p.env_base = e->cfg.env_index_base;
   p.t = e->t;
   p.k = e->k;
@@ -229,8 +235,19 @@ int launch_step_tma(const mgym_env* ce, const KernelParams& p_in, cudaStream_t s
   uint64_t blocks = tiles < slots ? tiles : slots;
   if (blocks < 1) blocks = 1;
   p.work_counter = e->work + e->work_slot;
-  p.work_base = e->work_issued[e->work_slot];
-  e->work_issued[e->work_slot] += tiles + blocks;
+  if (p.t_dev && e->work_slot == 0) {
+    // device clock: the first ticket is read from clock[1], which moves on by this launch's tickets when the
+    // launch ends (fused) or when clock_advance_kernel runs after the call.  One TMA launch per call draws
+    // from counter 0 (the head of a ragged size, see dispatch_mode).
+    p.base_dev = e->clock + 1;
+    if (p.adv_clock)
+      p.adv_tickets = tiles + blocks;
+    else
+      e->call_tickets += tiles + blocks;
+  } else {
+    p.work_base = e->work_issued[e->work_slot];
+    e->work_issued[e->work_slot] += tiles + blocks;
+  }
   static const bool pdl = [] {
     const char* s = getenv("MGYM_NO_PDL");
     return !(s && atoi(s) != 0);
@@ -277,6 +294,7 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
     if (autor && use_tma() && p.n > TMA_TILE) {
       // ragged size: whole 1024-env tiles on the TMA kernel, the remaining (< 1024) envs on the vector kernel
       KernelParams head = p, tail = p;
+      head.adv_dt = 0;  // device clock: the tail launch (last of the call) moves the step index on
       head.n = p.n - p.n % TMA_TILE;
       tail.first = p.first + head.n;
       tail.n = p.n - head.n;
@@ -343,17 +361,37 @@ int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* m
 // The step index (Philox counter) and the tile-ticket base are host-side launch parameters that change with
 // every call, so a captured launch replayed from a CUDA graph would repeat one step's random draws and find its
 // tickets spent.  Refuse capture instead of returning wrong results.
-int refuse_capture(cudaStream_t st, const char* what) {
+bool is_capturing(cudaStream_t st) {
   cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
     cudaGetLastError();
-    return MGYM_OK;
+    return false;
   }
-  if (status != cudaStreamCaptureStatusNone)
+  return status != cudaStreamCaptureStatusNone;
+}
+
+// `capturable`: the call carries no per-call value when the handle keeps a device clock
+int refuse_capture(const mgym_env* e, cudaStream_t st, const char* what, bool capturable) {
+  if (!is_capturing(st)) return MGYM_OK;
+  if (capturable && e->cfg.device_clock) return MGYM_OK;
+  if (capturable)
     return fail(MGYM_ERR_BAD_ARGUMENT,
                 "%s: the stream is being captured into a CUDA graph; step index and tile tickets are per-call "
-                "launch parameters, a replay would be wrong (use mgym_rollout for fused multi-step launches)",
+                "launch parameters of this handle, a replay would be wrong (create the handle with "
+                "device_clock = 1, or use mgym_rollout for fused multi-step launches)",
                 what);
+  return fail(MGYM_ERR_BAD_ARGUMENT, "%s cannot be captured into a CUDA graph (it synchronises or depends on host state)",
+              what);
+}
+
+// device clock: enqueue t += dt, ticket base += the tickets this call's TMA launch drew
+int advance_clock(mgym_env* e, uint64_t dt, cudaStream_t st, bool fused = false) {
+  if (e->cfg.device_clock && !fused) {
+    clock_advance_kernel<<<1, 1, 0, st>>>(e->clock, dt, e->call_tickets);
+    MGYM_CUDA(cudaGetLastError());
+  }
+  e->call_tickets = 0;
+  e->t += dt;  // host mirror: exact only while no graph replays the call (mgym_step_index reads the device)
   return MGYM_OK;
 }
 
@@ -446,6 +484,7 @@ int mgym_config_default(int kind, mgym_config* cfg) {
   cfg->track_stats = 1;
   cfg->validate_actions = 0;
   cfg->env_index_base = 0;
+  cfg->device_clock = 0;
   switch (kind) {
     case MGYM_MOUNTAIN_CAR_CONTINUOUS_V0: cfg->max_episode_steps = 999; break;
     case MGYM_PENDULUM_V1: cfg->max_episode_steps = 200; break;
@@ -458,6 +497,7 @@ int mgym_config_default(int kind, mgym_config* cfg) {
 int mgym_destroy(mgym_env* e) {
   if (!e) return MGYM_OK;
   DeviceGuard guard(e->device);
+  cudaFree(e->clock);
   cudaFree(e->state);
   cudaFree(e->steps);
   cudaFree(e->sbt);
@@ -550,6 +590,8 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
     }
     MGYM_CUDA(cudaMalloc(&e->stats, 5 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMemset(e->stats, 0, 5 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMalloc(&e->clock, 3 * sizeof(unsigned long long)));
+    MGYM_CUDA(cudaMemset(e->clock, 0, 3 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMalloc(&e->work, 4 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMemset(e->work, 0, 4 * sizeof(unsigned long long)));
     MGYM_CUDA(cudaMalloc(&e->bad_action, sizeof(uint32_t)));
@@ -569,13 +611,31 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
 
 uint64_t mgym_num_envs(const mgym_env* e) { return e ? e->n : 0; }
 int mgym_kind_of(const mgym_env* e) { return e ? e->kind : MGYM_ERR_BAD_ARGUMENT; }
-uint64_t mgym_step_index(const mgym_env* e) { return e ? e->t : 0; }
+// With a device clock the authoritative step index is on the device (graph replays advance it without the
+// host's knowledge): this then synchronises the device and refreshes the host mirror.
+uint64_t mgym_step_index(const mgym_env* ce) {
+  if (!ce) return 0;
+  mgym_env* e = const_cast<mgym_env*>(ce);
+  if (e->cfg.device_clock) {
+    DeviceGuard guard(e->device);
+    unsigned long long t = e->t;
+    if (cudaDeviceSynchronize() == cudaSuccess &&
+        cudaMemcpy(&t, e->clock, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+      e->t = t;
+    else
+      cudaGetLastError();
+  }
+  return e->t;
+}
 float* mgym_state_ptr(mgym_env* e) { return e ? e->state : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
 // reset
 // ---------------------------------------------------------------------------------------------
 int mgym_reset_masked(mgym_env* e, const uint8_t* mask, float* obs_out, void* stream) {
+  if (e) {
+    if (int rc = refuse_capture(e, (cudaStream_t)stream, "mgym_reset", false)) return rc;  // reset index is host state
+  }
   if (!e) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_reset: env is NULL");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -731,6 +791,7 @@ size_t mgym_checkpoint_size(const mgym_env* e) {
 int mgym_checkpoint_save(mgym_env* e, void* blob, size_t blob_bytes, void* stream) {
   if (!e || !blob) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_save: NULL argument");
   if (blob_bytes < mgym_checkpoint_size(e)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_save: blob too small");
+  (void)mgym_step_index(e);  // device clock: refresh e->t from the device
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->n;
@@ -783,6 +844,11 @@ int mgym_checkpoint_load(mgym_env* e, const void* blob, size_t blob_bytes, void*
   MGYM_CUDA(cudaStreamSynchronize(st));
   e->seed = h.seed;
   e->t = h.t;
+  if (e->cfg.device_clock) {
+    const unsigned long long t = h.t;
+    MGYM_CUDA(cudaMemcpyAsync(e->clock, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+    MGYM_CUDA(cudaStreamSynchronize(st));
+  }
   e->n_resets = h.n_resets;
   return MGYM_OK;
 }
@@ -796,7 +862,8 @@ int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_ou
   e->work_slot = 0;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = refuse_capture(st, "mgym_step")) return rc;
+  if (int rc = refuse_capture(e, st, "mgym_step", true)) return rc;
+  e->call_tickets = 0;
   KernelParams p = base_params(e);
   p.actions = actions;
   // zero-copy observation: for kinds whose observation is the state, obs_out == state rows is a no-op
@@ -804,11 +871,13 @@ int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_ou
   p.reward_out = reward_out;
   p.flags_out = flags_out;
   p.final_obs_out = final_obs_out;
+  p.adv_clock = e->cfg.device_clock ? e->clock : nullptr;
+  p.adv_dt = 1;
   const bool vec4 = e->vec4 && aligned16(actions) && aligned16(obs_out) && aligned16(reward_out) &&
                     aligned16(flags_out) && aligned16(final_obs_out);
   int rc = dispatch<false>(e, p, vec4, st);
   if (rc != MGYM_OK) return rc;
-  e->t += 1;
+  if ((rc = advance_clock(e, 1, st, /*fused=*/true)) != MGYM_OK) return rc;
   return check_bad_action(e, st);
 }
 
@@ -818,7 +887,8 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   if (K == 0) return MGYM_OK;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = refuse_capture(st, "mgym_rollout")) return rc;
+  if (int rc = refuse_capture(e, st, "mgym_rollout", true)) return rc;
+  e->call_tickets = 0;
   KernelParams p = base_params(e);
   p.actions = actions;
   p.obs_out = obs_traj;
@@ -826,6 +896,8 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   p.flags_out = flags_traj;
   p.done_count = done_count_out;
   p.K = K;
+  p.adv_clock = e->cfg.device_clock ? e->clock : nullptr;
+  p.adv_dt = K;
   if (done_count_out) MGYM_CUDA(cudaMemsetAsync(done_count_out, 0, sizeof(unsigned long long), st));
   const bool vec4 = e->vec4 && aligned16(actions) && aligned16(obs_traj) && aligned16(reward_traj) &&
                     aligned16(flags_traj);
@@ -835,7 +907,7 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   MGYM_CUDA(cudaMemsetAsync(e->work + 3, 0, sizeof(unsigned long long), st));
   int rc = dispatch<true>(e, p, vec4, st);
   if (rc != MGYM_OK) return rc;
-  e->t += K;
+  if ((rc = advance_clock(e, K, st, /*fused=*/true)) != MGYM_OK) return rc;
   return check_bad_action(e, st);
 }
 
@@ -843,14 +915,16 @@ int mgym_sample_actions(mgym_env* e, void* actions_out, void* stream) {
   if (!e || !actions_out) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_sample_actions: NULL argument");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = refuse_capture(e, st, "mgym_sample_actions", true)) return rc;
   const unsigned blocks = (unsigned)((e->n + 255) / 256);
   const uint64_t base = e->cfg.env_index_base;
+  const unsigned long long* td = e->cfg.device_clock ? e->clock : nullptr;
   switch (e->kind) {
-    case 0: sample_actions_kernel<0><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
-    case 1: sample_actions_kernel<1><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
-    case 2: sample_actions_kernel<2><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t); break;
-    case 3: sample_actions_kernel<3><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t); break;
-    default: sample_actions_kernel<4><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t); break;
+    case 0: sample_actions_kernel<0><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t, td); break;
+    case 1: sample_actions_kernel<1><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t, td); break;
+    case 2: sample_actions_kernel<2><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t, td); break;
+    case 3: sample_actions_kernel<3><<<blocks, 256, 0, st>>>((float*)actions_out, e->n, e->seed, base, e->t, td); break;
+    default: sample_actions_kernel<4><<<blocks, 256, 0, st>>>((uint8_t*)actions_out, e->n, e->seed, base, e->t, td); break;
   }
   MGYM_CUDA(cudaGetLastError());
   return MGYM_OK;
@@ -864,6 +938,8 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
   if (!e || !actions_host) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_step_host: NULL argument");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = refuse_capture(e, st, "mgym_step_host", false)) return rc;
+  e->call_tickets = 0;
   const size_t n = (size_t)e->n;
   const int od = kObsDim[e->kind];
   const size_t act = action_size(e->kind), asz = act * n, osz = sizeof(float) * od * n;
@@ -917,7 +993,7 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
     }
   }
   e->work_slot = 0;
-  e->t += 1;
+  if (int rc = advance_clock(e, 1, st)) return rc;
   MGYM_CUDA(cudaStreamSynchronize(st));
   return check_bad_action(e, st);
 }

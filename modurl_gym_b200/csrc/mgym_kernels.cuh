@@ -70,6 +70,16 @@ struct KernelParams {
   uint32_t* bad_action;            // validate_actions: set to 1 on an out-of-range discrete action
   unsigned long long* work_counter;  // TMA step kernel: tile tickets (monotonic across launches)
   uint64_t work_base;                // first ticket of this launch
+  // Device clock (handles created with device_clock = 1, the CUDA-graph-capturable mode): the step index and
+  // the first ticket live in device memory and are advanced by clock_advance_kernel after every call, so a
+  // captured launch carries no per-call value.  Null = use `t` / `work_base` above.
+  const unsigned long long* t_dev;
+  const unsigned long long* base_dev;
+  // Fused advance of that clock: the last CTA of the launch to finish adds adv_dt / adv_tickets (every CTA
+  // has read the clock by then; the next launch reads it only after this grid has completed).  clock[2] counts
+  // finished CTAs.  Null = the host enqueues clock_advance_kernel instead (mgym_step_host's chunked launches).
+  unsigned long long* adv_clock;
+  uint64_t adv_dt, adv_tickets;
   uint64_t n;      // envs covered by this launch
   uint64_t first;  // index (within the handle) of the first of them
   uint64_t ld;     // row stride of every SoA buffer = envs in the handle
@@ -78,6 +88,23 @@ struct KernelParams {
   PhiloxKeys keys;  // round keys of `seed`
   EnvConsts k;
 };
+
+__device__ __forceinline__ uint64_t launch_t(const KernelParams& p) { return p.t_dev ? *p.t_dev : p.t; }
+__device__ __forceinline__ uint64_t launch_work_base(const KernelParams& p) {
+  return p.base_dev ? *p.base_dev : p.work_base;
+}
+
+// call after the CTA's last use of the clock (all threads may call; thread 0 acts)
+__device__ __forceinline__ void fused_clock_advance(const KernelParams& p) {
+  if (p.adv_clock && threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(p.adv_clock + 2, 1ull) + 1ull;
+    if (done == gridDim.x) {
+      p.adv_clock[2] = 0ull;
+      p.adv_clock[0] += p.adv_dt;
+      p.adv_clock[1] += p.adv_tickets;
+    }
+  }
+}
 
 // ---- vector load/store of V consecutive elements --------------------------------------
 template <typename T, int V>
@@ -424,6 +451,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
   const bool want_final = p.final_obs_out != nullptr;
+  const uint64_t t_now = launch_t(p);
 
   for (uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; grp < groups; grp += stride) {
     const uint64_t base = p.first + grp * V;
@@ -456,9 +484,9 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
       }
     }
     if (want_final)
-      step_group<KIND, V, AUTO, true>(p, true, base, p.t, action, track_ret, g, acc);
+      step_group<KIND, V, AUTO, true>(p, true, base, t_now, action, track_ret, g, acc);
     else
-      step_group<KIND, V, AUTO, false>(p, true, base, p.t, action, track_ret, g, acc);
+      step_group<KIND, V, AUTO, false>(p, true, base, t_now, action, track_ret, g, acc);
 
     {
       Vec<float, V> s[SD];
@@ -519,6 +547,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
     }
   }
   if constexpr (AUTO) stats_flush<KIND>(acc, p);
+  fused_clock_advance(p);
 }
 
 // =============================================================================================
@@ -650,6 +679,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   // flushed.  Our own dependents may start their prologue as soon as they find room.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
+  const uint64_t t_now = launch_t(p), work_base = launch_work_base(p);  // only after the wait: see t_dev
 
   if (warp == TMA_CONSUMER_WARPS) {
     // ---------------- producer ----------------
@@ -662,7 +692,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       for (uint32_t it = 0;; ++it) {
         const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
         tma::mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);  // first round passes at once
-        const uint64_t tile = atomicAdd(p.work_counter, 1ull) - p.work_base;
+        const uint64_t tile = atomicAdd(p.work_counter, 1ull) - work_base;
         const uint32_t bar = full0 + 8 * s, dst = data0 + s * L::STAGE_BYTES;
         tile_slot[s] = tile;
         if (tile >= n_tiles) {  // out of work: tell the consumers and stop
@@ -698,11 +728,11 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         const uint64_t gid = p.env_base + local;
         float ns[SD];
         if (p.reset_pool) {
-          const uint64_t k = (gid + p.t) % p.pool_len;
+          const uint64_t k = (gid + t_now) % p.pool_len;
 #pragma unroll
           for (int c = 0; c < SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + k];
         } else {
-          E::reset(philox_env(p.keys, gid, p.t, TAG_AUTO_RESET), ns);
+          E::reset(philox_env(p.keys, gid, t_now, TAG_AUTO_RESET), ns);
         }
 #pragma unroll
         for (int c = 0; c < SD; ++c) p.state[(uint64_t)c * p.ld + local] = ns[c];
@@ -780,9 +810,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       }
 #else
       if (want_final)
-        step_group<KIND, V, true, true, true, RESET_BY_CALLER>(p, true, base, p.t, action, track_ret, g, acc);
+        step_group<KIND, V, true, true, true, RESET_BY_CALLER>(p, true, base, t_now, action, track_ret, g, acc);
       else
-        step_group<KIND, V, true, false, true, RESET_BY_CALLER>(p, true, base, p.t, action, track_ret, g, acc);
+        step_group<KIND, V, true, false, true, RESET_BY_CALLER>(p, true, base, t_now, action, track_ret, g, acc);
 #endif
       // Everything about this lane's finished envs sits in one branch: statistics from the packed flags word,
       // counters cleared, and their index inside the tile appended to the reset queue.
@@ -853,6 +883,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     }
   }
   stats_flush<KIND>(acc, p);
+  fused_clock_advance(p);
 }
 
 // =============================================================================================
@@ -884,6 +915,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   const bool policy = p.actions == nullptr;
   const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
   const uint32_t lane = threadIdx.x & 31;
+  const uint64_t t_first = launch_t(p);
 
   // Warp tiles (32 lanes x V envs) are handed out by the global ticket counter, like the tiles of the step
   // kernel: faster warps take more, and the trip count stays warp-uniform so every lane reaches the votes.
@@ -974,7 +1006,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     auto one_step = [&](auto trusted_tag, uint32_t kk, const RawActions<act_t, V>& a_cur) -> bool {
       constexpr bool TRUSTED = decltype(trusted_tag)::value;
       bool still = true;
-      const uint64_t t = p.t + kk;
+      const uint64_t t = t_first + kk;
       act_t action[V];
       if (policy) {
         // Space::sample: one Philox block serves 4 consecutive envs (global group g >> 2)
@@ -1111,6 +1143,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   }
   acc.done_steps = dones;
   stats_flush<KIND>(acc, p);
+  fused_clock_advance(p);
 }
 
 // =============================================================================================
@@ -1167,11 +1200,18 @@ __global__ void obs_kernel(const float* state, float* obs_out, uint64_t n) {
   for (int c = 0; c < E::OD; ++c) obs_out[(uint64_t)c * n + i] = obs[c];
 }
 
+// device clock: t += dt, ticket base += tickets (one thread, enqueued after the launches of a call)
+__global__ void clock_advance_kernel(unsigned long long* clock, unsigned long long dt, unsigned long long tickets) {
+  clock[0] += dt;
+  clock[1] += tickets;
+}
+
 template <int KIND>
 __global__ void sample_actions_kernel(typename Env<KIND>::act_t* out, uint64_t n, uint64_t seed, uint64_t env_base,
-                                      uint64_t t) {
+                                      uint64_t t, const unsigned long long* t_dev) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (t_dev) t = *t_dev;
   const uint64_t g = env_base + i;
   const uint4 w = philox_env(seed, g >> 2, t, TAG_ACTION);
   const uint32_t ws[4] = {w.x, w.y, w.z, w.w};

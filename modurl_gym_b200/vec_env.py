@@ -77,7 +77,7 @@ class GpuVecEnv:
 
     def __init__(self, kind, num_envs, device=0, seed=0, auto_reset=True, max_episode_steps=None,
                  sutton_barto_reward=False, is_euler=True, goal_velocity=0.0, track_stats=True,
-                 validate_actions=False, env_index_base=0):
+                 validate_actions=False, env_index_base=0, graph_capturable=False):
         self._lib = _lib.load()
         self.kind = KINDS[kind] if isinstance(kind, str) else int(kind)
         if isinstance(device, torch.device):
@@ -95,6 +95,9 @@ class GpuVecEnv:
         cfg.track_stats = int(bool(track_stats))
         cfg.validate_actions = int(bool(validate_actions))
         cfg.env_index_base = int(env_index_base)
+        # device_clock: step index and tile tickets live on the device, so step / rollout / sample_actions can be
+        # captured into a CUDA graph (torch.cuda.graph) and replayed; one extra one-thread launch per call
+        cfg.device_clock = int(bool(graph_capturable))
         self.config = cfg
         self.auto_reset = bool(auto_reset)
         self._h = C.c_void_p()
