@@ -212,12 +212,12 @@ int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, u
 }
 
 // TMA-staged step kernel (auto-reset, vector path, N a multiple of the 128-env warp tile)
-template <int KIND, int CNT>
+template <int KIND, int CNT, bool AUTO = true>
 int launch_step_tma(const mgym_env* ce, const KernelParams& p_in, cudaStream_t st) {
   mgym_env* e = const_cast<mgym_env*>(ce);  // ticket accounting
   KernelParams p = p_in;
-  using L = TmaLayout<KIND, CNT>;
-  auto kernel = step_kernel_tma<KIND, CNT>;
+  using L = TmaLayout<KIND, CNT, AUTO>;
+  auto kernel = step_kernel_tma<KIND, CNT, AUTO>;
   constexpr int threads = TMA_THREADS;
   // the opt-in to > 48 KB of dynamic shared memory and the occupancy are per device
   static int cached_per_sm[kMaxDevices] = {};
@@ -280,6 +280,8 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   const uint64_t groups = p.n / V;
   const bool autor = e->cfg.auto_reset != 0;
   if constexpr (!ROLLOUT && V == 4) {
+    // manual mode (the reference's protocol): counters are 32-bit, CartPole adds steps_beyond_terminated
+    if (!autor && use_tma() && p.n % TMA_TILE == 0) return launch_step_tma<KIND, CNT_U32, false>(e, p, st);
     if (autor && use_tma() && p.n % TMA_TILE == 0) {
       if constexpr (KIND == 0) {
         return launch_step_tma<KIND, CNT_U16>(e, p, st);
@@ -291,7 +293,7 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
         }
       }
     }
-    if (autor && use_tma() && p.n > TMA_TILE) {
+    if (use_tma() && p.n > TMA_TILE) {
       // ragged size: whole 1024-env tiles on the TMA kernel, the remaining (< 1024) envs on the vector kernel
       KernelParams head = p, tail = p;
       head.adv_dt = 0;  // device clock: the tail launch (last of the call) moves the step index on
@@ -348,6 +350,16 @@ int dispatch(const mgym_env* e, const KernelParams& p, bool vec4, cudaStream_t s
 
 template <int KIND>
 int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* mask, cudaStream_t st) {
+  if (mask && !p.obs_out && p.first == 0 && p.n % 16 == 0 && aligned16(mask)) {
+    const unsigned blocks = (unsigned)((p.n / 16 + 255) / 256);
+    switch (e->cnt_mode) {
+      case CNT_NONE: reset_sparse_kernel<KIND, CNT_NONE><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+      case CNT_U16: reset_sparse_kernel<KIND, CNT_U16><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+      default: reset_sparse_kernel<KIND, CNT_U32><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+    }
+    MGYM_CUDA(cudaGetLastError());
+    return MGYM_OK;
+  }
   const unsigned blocks = (unsigned)((p.n + 255) / 256);
   switch (e->cnt_mode) {
     case CNT_NONE: reset_kernel<KIND, CNT_NONE><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;

@@ -614,7 +614,7 @@ constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 2) * 32;  // + one producer wa
 constexpr int TMA_RESET_BUFFERS = 2;                         // request queues in flight
 constexpr int TMA_TILE = TMA_CONSUMER_WARPS * 32 * 4;       // envs per CTA tile: 256 consumer threads x V=4
 
-template <int KIND, int CNT>
+template <int KIND, int CNT, bool AUTO = true>
 struct TmaLayout {
   using E = Env<KIND>;
   static constexpr uint32_t ROW = TMA_TILE * 4;  // one f32 row of a tile
@@ -623,8 +623,11 @@ struct TmaLayout {
   static constexpr uint32_t OFF_CNT = OFF_ACT + ACT_BYTES;
   static constexpr uint32_t CNT_BYTES = CNT == CNT_NONE ? 0 : TMA_TILE * sizeof(typename CounterType<CNT>::type);
   static constexpr uint32_t OFF_RET = OFF_CNT + CNT_BYTES;
-  static constexpr uint32_t RET_BYTES = E::ANALYTIC_RETURN ? 0 : ROW;
-  static constexpr uint32_t STAGE_BYTES = (OFF_RET + RET_BYTES + 127u) & ~127u;
+  static constexpr uint32_t RET_BYTES = (E::ANALYTIC_RETURN || !AUTO) ? 0 : ROW;
+  // manual CartPole also carries steps_beyond_terminated (cartpole.rs:27)
+  static constexpr uint32_t OFF_SBT = OFF_RET + RET_BYTES;
+  static constexpr uint32_t SBT_BYTES = (!AUTO && KIND == 0) ? ROW : 0;
+  static constexpr uint32_t STAGE_BYTES = (OFF_SBT + SBT_BYTES + 127u) & ~127u;
   static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES], tile id of each stage
   static_assert(24 * TMA_STAGES <= 128, "barriers and tile ids must fit BAR_BYTES");
   // reset queues: per buffer {q_full, q_empty mbarriers, tile id, count} (32 B) + TMA_TILE uint16 env indices
@@ -646,10 +649,14 @@ struct TmaLayout {
 // next.  The reset warp then draws the new states with all 32 lanes busy (46 per tile on average = 2
 // passes per 1024 envs instead of 10) and patches them into the state rows (and obs_out) in global memory.
 // Consumers never wait for it except to reuse a queue buffer two tiles later.
-template <int KIND, int CNT>
+//
+// AUTO = false is the reference's own protocol (no same-step reset: the caller resets what finished,
+// cartpole.rs:468-470): the same pipeline with steps_beyond_terminated as one more row and nothing ever queued
+// for the reset warp.
+template <int KIND, int CNT, bool AUTO = true>
 __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_tma(const __grid_constant__ KernelParams p) {
   using E = Env<KIND>;
-  using L = TmaLayout<KIND, CNT>;
+  using L = TmaLayout<KIND, CNT, AUTO>;
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD, V = 4;
@@ -669,8 +676,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   auto q_items = [&](uint32_t b) { return reinterpret_cast<uint16_t*>(queue_ptr + b * QSTRIDE + 32); };
   const uint32_t data0 = smem_base + L::BAR_BYTES;
   const uint64_t n_tiles = p.n / TMA_TILE;
-  const bool track_ret = !E::ANALYTIC_RETURN && p.ep_return != nullptr;
+  const bool track_ret = AUTO && !E::ANALYTIC_RETURN && p.ep_return != nullptr;
   const bool want_final = p.final_obs_out != nullptr;
+  constexpr bool HAS_SBT = !AUTO && KIND == 0;
   StatAcc acc;
 
   if (threadIdx.x == 0) {
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
     // tickets [work_base, work_base + n_tiles + gridDim.x): each CTA draws exactly one ticket past the end.
     if (lane == 0) {
       const act_t* actions = reinterpret_cast<const act_t*>(p.actions);
-      const uint32_t tx = SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u);
+      const uint32_t tx = SD * L::ROW + L::ACT_BYTES + L::CNT_BYTES + (track_ret ? L::ROW : 0u) + L::SBT_BYTES;
       for (uint32_t it = 0;; ++it) {
         const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
         tma::mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);  // first round passes at once
@@ -719,9 +727,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
         if constexpr (CNT != CNT_NONE)
           tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
-        if constexpr (!E::ANALYTIC_RETURN) {
+        if constexpr (!E::ANALYTIC_RETURN && AUTO) {
           if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
         }
+        if constexpr (HAS_SBT) tma::bulk_g2s(dst + L::OFF_SBT, p.sbt + e0, L::ROW, bar);
       }
     }
     __syncwarp();
@@ -792,9 +801,11 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         Vec<cnt_t, V> cnt;
         if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + tid * V);
         Vec<float, V> er;
-        if constexpr (!E::ANALYTIC_RETURN) {
+        if constexpr (!E::ANALYTIC_RETURN && AUTO) {
           if (track_ret) er = ldv<float, V>(reinterpret_cast<const float*>(st + L::OFF_RET) + tid * V);
         }
+        Vec<uint32_t, V> sb;
+        if constexpr (HAS_SBT) sb = ldv<uint32_t, V>(reinterpret_cast<const uint32_t*>(st + L::OFF_SBT) + tid * V);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
 #pragma unroll
@@ -803,8 +814,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
           g.steps[v] = 0;
           g.sbt[v] = SBT_NONE;
           if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+          if constexpr (HAS_SBT) g.sbt[v] = sb.v[v];
           g.ret[v] = 0.0f;
-          if constexpr (!E::ANALYTIC_RETURN) g.ret[v] = track_ret ? er.v[v] : 0.0f;
+          if constexpr (!E::ANALYTIC_RETURN && AUTO) g.ret[v] = track_ret ? er.v[v] : 0.0f;
           if constexpr (!E::CONTINUOUS) {
             if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
           }
@@ -823,16 +835,17 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       }
 #else
       if (want_final)
-        step_group<KIND, V, true, true, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret, g,
+        step_group<KIND, V, AUTO, true, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret, g,
                                                                                    acc);
       else
-        step_group<KIND, V, true, false, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret,
+        step_group<KIND, V, AUTO, false, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret,
                                                                                     g, acc);
 #endif
       // Everything about this lane's finished envs sits in one branch: statistics from the packed flags word,
       // counters cleared, and their index inside the tile appended to the reset queue.
       const uint32_t fw = packed_flags<KIND, V>(g);
-      const uint32_t fin = MGYM_EXP_MEMONLY ? 0u : fw;  // the memory-only experiment finishes nothing
+      // the memory-only experiment finishes nothing; in manual mode finished envs wait for the caller's reset
+      const uint32_t fin = (MGYM_EXP_MEMONLY || !AUTO) ? 0u : fw;
       if (fin) {
         tally_packed<KIND, V, true>(fin, g, acc);
         uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc((fin | (fin >> 1)) & 0x01010101u));
@@ -860,13 +873,19 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
         stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
       }
-      if constexpr (!E::ANALYTIC_RETURN) {
+      if constexpr (!E::ANALYTIC_RETURN && AUTO) {
         if (track_ret) {
           Vec<float, V> er;
 #pragma unroll
           for (int v = 0; v < V; ++v) er.v[v] = g.ret[v];
           stv<float, V>(p.ep_return + base, er);
         }
+      }
+      if constexpr (HAS_SBT) {
+        Vec<uint32_t, V> sbo;
+#pragma unroll
+        for (int v = 0; v < V; ++v) sbo.v[v] = g.sbt[v];
+        stv<uint32_t, V>(p.sbt + base, sbo);
       }
       if (p.obs_out) {
 #pragma unroll
@@ -897,7 +916,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       if (lane == 0) tma::mbar_arrive(q_full);
     }
   }
-  stats_flush<KIND>(acc, p);
+  if constexpr (AUTO) stats_flush<KIND>(acc, p);
   fused_clock_advance(p);
 }
 
@@ -1164,24 +1183,12 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
 // =============================================================================================
 // cold kernels: reset, observation, action sampling, counter conversion
 // =============================================================================================
+// Gym::reset of env i (cartpole.rs:238-249, mountain_car.rs:279-291): new state, counters cleared, observation out
 template <int KIND, int CNT>
-__global__ void reset_kernel(const KernelParams p, const uint8_t* mask, uint64_t reset_index) {
+__device__ __forceinline__ void reset_one(const KernelParams& p, uint64_t i, uint64_t reset_index) {
   using E = Env<KIND>;
   using cnt_t = typename CounterType<CNT>::type;
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= p.n) return;
-  const uint64_t i = p.first + j;
   float st[E::SD], obs[E::OD];
-  if (mask && !mask[i]) {
-    if (p.obs_out) {
-#pragma unroll
-      for (int c = 0; c < E::SD; ++c) st[c] = p.state[(uint64_t)c * p.ld + i];
-      E::obs(st, obs);
-#pragma unroll
-      for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.ld + i] = obs[c];
-    }
-    return;
-  }
   const uint64_t g = p.env_base + i;
   if (p.reset_pool) {
     const uint64_t j = (g + reset_index) % p.pool_len;
@@ -1200,6 +1207,60 @@ __global__ void reset_kernel(const KernelParams p, const uint8_t* mask, uint64_t
 #pragma unroll
     for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.ld + i] = obs[c];
   }
+}
+
+template <int KIND, int CNT>
+__global__ void reset_kernel(const KernelParams p, const uint8_t* mask, uint64_t reset_index) {
+  using E = Env<KIND>;
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.n) return;
+  const uint64_t i = p.first + j;
+  if (mask && !mask[i]) {
+    if (p.obs_out) {
+      float st[E::SD], obs[E::OD];
+#pragma unroll
+      for (int c = 0; c < E::SD; ++c) st[c] = p.state[(uint64_t)c * p.ld + i];
+      E::obs(st, obs);
+#pragma unroll
+      for (int c = 0; c < E::OD; ++c) p.obs_out[(uint64_t)c * p.ld + i] = obs[c];
+    }
+    return;
+  }
+  reset_one<KIND, CNT>(p, i, reset_index);
+}
+
+// Masked reset without an observation output -- the caller's `if done { env.reset() }` after a manual-mode step
+// (cartpole.rs:468-470), where few envs are selected: each thread scans 16 mask bytes with one 128-bit load and
+// only then touches the envs whose byte is set (the one-thread-per-env form spends its time on 1-byte loads).
+// Requires first == 0, n % 16 == 0 and a 16-byte-aligned mask.
+template <int KIND, int CNT>
+__global__ void __launch_bounds__(256) reset_sparse_kernel(const KernelParams p, const uint8_t* mask, uint64_t reset_index) {
+  // Each warp scans 512 envs (one 128-bit mask load per lane), queues the selected ones in shared memory and
+  // then resets them with all lanes busy, whatever their distribution over the lanes' 16-env spans.
+  __shared__ uint16_t queue[8][512];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 16-env span of this lane
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);
+  if (j * 16 < p.n) m = reinterpret_cast<const uint4*>(mask)[j];
+  const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+  uint32_t bits = 0;  // bit b = env b of the span is selected
+#pragma unroll
+  for (int b = 0; b < 16; ++b) bits |= ((words[b >> 2] >> (8 * (b & 3))) & 0xffu) ? (1u << b) : 0u;
+  if (__ballot_sync(0xffffffffu, bits != 0u) == 0u) return;
+  // exclusive prefix sum of the per-lane counts
+  const uint32_t mine = __popc(bits);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += up;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t pos = incl - mine;
+  for (uint32_t rest = bits; rest; rest &= rest - 1) queue[warp][pos++] = (uint16_t)(lane * 16 + (__ffs(rest) - 1));
+  __syncwarp();
+  const uint64_t warp_base = (j - lane) * 16;
+  for (uint32_t k = lane; k < total; k += 32) reset_one<KIND, CNT>(p, warp_base + queue[warp][k], reset_index);
 }
 
 template <int KIND>

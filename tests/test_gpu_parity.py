@@ -306,10 +306,11 @@ def test_auto_reset_injected_pool_and_final_obs(gym, oracle, kind):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", range(5))
 @pytest.mark.parametrize("sb", [False, True])
-def test_manual_mode_parity(gym, oracle, kind, sb):
+@pytest.mark.parametrize("n", [1024, 3076, 515])  # one TMA tile; three tiles + a 4-env tail; scalar lanes
+def test_manual_mode_parity(gym, oracle, kind, sb, n):
     if sb and kind != 0:
         pytest.skip("sutton_barto_reward is a CartPole option")
-    n, T = 1024, 120
+    T = 120
     rng = np.random.default_rng(50 + kind)
     env = gym.GpuVecEnv(kind, n, auto_reset=False, seed=11, sutton_barto_reward=sb)
     ref = oracle.VecState(kind, n, auto_reset=0, seed=11, sutton_barto_reward=int(sb))

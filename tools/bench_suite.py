@@ -74,6 +74,8 @@ def main():
         obs = torch.empty((K, env.obs_dim, n), device="cuda")
         zero_copy = kind in (0, 1, 2)
         for mode in args.modes.split(","):
+            if mode == "manual":
+                continue
             if mode == "step":
                 i = [0]
 
@@ -100,6 +102,25 @@ def main():
                               "ms_per_launch": sec * 1e3, "env_steps_per_s": rate, "bytes_per_env_step": bytes_per,
                               "algorithmic_GBps": gbs, "frac_of_measured_hbm_peak": gbs / pk,
                               "mean_episode_length": s.length_sum / max(s.episodes, 1)}), flush=True)
+        if "manual" in args.modes.split(","):
+            # the reference's own protocol, batched: Gym::step without auto-reset, then the caller resets the envs
+            # that returned done or truncated (cartpole.rs:468-470) -- two launches per step
+            menv = m.GpuVecEnv(kind, n, seed=0x5EED, auto_reset=False)
+            menv.reset()
+            i = [0]
+
+            def fn():
+                k = i[0] % K
+                menv.step_raw(acts[k], None if zero_copy else obs[0], reward[0], flags[0])
+                menv.reset(mask=flags[0])
+                i[0] += 1
+
+            sec = timed(fn, args.reps * 4)
+            rate = n / sec
+            print(json.dumps({"kind": NAMES[kind], "mode": "manual step + masked reset", "num_envs": n,
+                              "steps_per_launch": 1, "ms_per_launch": sec * 1e3, "env_steps_per_s": rate}), flush=True)
+            menv.close()
+            del menv
         env.close()
         del env, acts, reward, flags, obs
         torch.cuda.empty_cache()
