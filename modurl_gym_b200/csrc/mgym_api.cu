@@ -385,6 +385,9 @@ bool is_capturing(cudaStream_t st) {
 // `capturable`: the call carries no per-call value when the handle keeps a device clock
 int refuse_capture(const mgym_env* e, cudaStream_t st, const char* what, bool capturable) {
   if (!is_capturing(st)) return MGYM_OK;
+  if (capturable && e->cfg.device_clock && e->cfg.validate_actions)
+    return fail(MGYM_ERR_BAD_ARGUMENT, "%s: validate_actions reads a flag back after every call, which a captured "
+                "stream cannot do; create the handle without it", what);
   if (capturable && e->cfg.device_clock) return MGYM_OK;
   if (capturable)
     return fail(MGYM_ERR_BAD_ARGUMENT,

@@ -1100,7 +1100,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
           tally_packed<KIND, V, !kLenIdentity>(wf, g, acc);
           uint32_t pending = 0;
 #pragma unroll
-          for (int v = 0; v < V; ++v) pending |= ((w >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
+          for (int v = 0; v < V; ++v) pending |= ((wf >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
           reset_pending<KIND, V>(p, base, t, pending, g);
           if constexpr (TRUSTED && E::HAS_TRUSTED) {
             if (p.reset_pool) still = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));
