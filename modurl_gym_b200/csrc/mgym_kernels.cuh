@@ -3,8 +3,10 @@
 //   step_kernel_tma one Gym::step per env per launch, the headline form: a producer warp stages 1024-env
 //                   tiles (state rows, actions, counters) into a shared-memory ring with cp.async.bulk,
 //                   eight consumer warps step 4 consecutive envs per thread and store with 128-bit
-//                   stores.  HBM-bound (profiles/README.md).
-//   step_kernel     the same step with plain vector loads: manual mode, ragged N, unaligned buffers.
+//                   stores, a reset warp draws the reset states of the envs that finished.  HBM-bound
+//                   (profiles/README.md).  Auto-reset and manual (the reference's protocol) forms.
+//   step_kernel     the same step with plain vector loads: ragged N (scalar lanes, sub-tile tails),
+//                   unaligned buffers.
 //   rollout_kernel  K fused steps: state and counters stay in registers, only the trajectory
 //                   (obs / reward / flags) is written, actions are read or drawn from Philox.
 //
@@ -252,11 +254,10 @@ struct Group {
 
 // What step_group does with the envs that finished (AUTO only):
 //   RESET_IN_PLACE  tallies them and draws their reset states right away (per-call step, LDG form)
-//   RESET_DEFERRED  tallies them, clears their counters and returns their slot mask: the TMA step kernel
-//                   hands them to its reset warp
-//   RESET_BY_CALLER neither tallies nor resets: the rollout kernel does both behind ONE warp vote, so a
-//                   step in which no env of the warp finished pays nothing for statistics or resets
-enum ResetMode : int { RESET_IN_PLACE = 0, RESET_DEFERRED = 1, RESET_BY_CALLER = 2 };
+//   RESET_BY_CALLER neither tallies nor resets.  The rollout kernel does both behind ONE warp vote, so a step in
+//                   which no env of the warp finished pays nothing for statistics or resets; the TMA step kernel
+//                   tallies from the packed flags word and hands the finished envs to its reset warp.
+enum ResetMode : int { RESET_IN_PLACE = 0, RESET_BY_CALLER = 2 };
 
 // Draws the reset states of the slots in `pending` (bit v = slot v), one slot per lane per pass.
 template <int KIND, int V>
@@ -426,16 +427,6 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
         if (tally) acc.return_sum += (double)g.ret[v];
       }
     }
-  }
-  if constexpr (AUTO && RESET == RESET_DEFERRED) {
-    // The caller hands the finished envs to the reset warp; only what needs no random draw is done here.
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const bool hit = (pending >> v) & 1u;
-      g.steps[v] = hit ? 0u : g.steps[v];
-      g.ret[v] = hit ? 0.0f : g.ret[v];
-    }
-    return pending;
   }
   if constexpr (AUTO && RESET == RESET_IN_PLACE) reset_pending<KIND, V>(p, base, t, pending, g);
   return 0u;
@@ -1125,6 +1116,21 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     auto step_any = [&](uint32_t kk, const RawActions<act_t, V>& a_cur) {
       if constexpr (E::HAS_TRUSTED) {
         if (trusted) {
+          if constexpr (E::CONTINUOUS) {
+            // a NaN action would break the invariant: the sum of the lane's actions is NaN iff one of them is
+            // (or +inf meets -inf, which only costs this one checked step); such a step runs checked, and the
+            // invariant is tested again after it
+            if (!policy) {
+              float sum = a_cur.get(0);
+#pragma unroll
+              for (int v = 1; v < V; ++v) sum += a_cur.get(v);
+              if (__any_sync(0xffffffffu, sum != sum)) {
+                one_step(std::false_type{}, kk, a_cur);
+                trusted = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));
+                return;
+              }
+            }
+          }
           trusted = one_step(std::true_type{}, kk, a_cur);
           return;
         }

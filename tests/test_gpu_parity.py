@@ -643,6 +643,30 @@ def test_mountain_car_rollout_leaves_trusted_loop_on_bad_pool_state(gym, oracle)
     env.close()
 
 
+def test_mountain_car_continuous_rollout_survives_nan_and_inf_actions(gym, oracle):
+    """MountainCarContinuous runs the trusted loop too, which additionally needs actions that are not NaN: a warp
+    that meets one runs that step checked and re-tests its invariant.  NaN, +-inf and huge actions are sprinkled
+    over ordinary ones; flags, observations and rewards must match the oracle (NaN where it has NaN)."""
+    n, K = 4096, 20
+    rng = np.random.default_rng(4242)
+    env = gym.GpuVecEnv(2, n, auto_reset=True, seed=13)
+    ref = oracle.VecState(2, n, auto_reset=1, seed=13)
+    env.reset(), ref.reset()
+    with np.errstate(all="ignore"):
+        for chunk in range(3):
+            a = random_actions(rng, 2, (K, n))
+            weird = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0, -0.0], dtype=np.float32)
+            hit = rng.random((K, n)) < (0.0 if chunk == 0 else 0.002)   # first chunk: pure trusted loop
+            a[hit] = rng.choice(weird, size=int(hit.sum()))
+            out = env.rollout(K, dev(a))
+            o, r, f, dc = ref.rollout(K, a)
+            assert_bit_equal(host(out.flags), f, f"flags chunk {chunk}")
+            assert_equal_or_both_nan(host(out.obs), o, f"obs chunk {chunk}")
+            assert_equal_or_both_nan(host(out.reward), r, f"reward chunk {chunk}")
+            assert int(out.done_count.item()) == dc
+    env.close()
+
+
 def test_mountain_car_1000_step_chunked_rollout(gym, oracle):
     """BASELINE configs[2]: a 1000-step MountainCar rollout run as 32-step launches over one reused ring equals
     the oracle's single 1000-step rollout (flags, rewards, observations of every step, final state)."""
