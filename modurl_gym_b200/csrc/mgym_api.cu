@@ -992,11 +992,9 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
     p.flags_out = flags_host ? e->h_flags : nullptr;
     int rc = dispatch<false>(e, p, e->vec4, cs);
     if (rc != MGYM_OK) return rc;
-    if (obs_host) {
-      for (int r = 0; r < od; ++r)
-        MGYM_CUDA(cudaMemcpyAsync(obs_host + (size_t)r * n + b, dev_obs + (size_t)r * n + b, sizeof(float) * cnt,
-                                  cudaMemcpyDeviceToHost, cs));
-    }
+    if (obs_host)  // all od rows of this chunk as ONE strided copy (fewer copy-engine round trips than od copies)
+      MGYM_CUDA(cudaMemcpy2DAsync(obs_host + b, sizeof(float) * n, dev_obs + b, sizeof(float) * n, sizeof(float) * cnt,
+                                  (size_t)od, cudaMemcpyDeviceToHost, cs));
     if (reward_host)
       MGYM_CUDA(cudaMemcpyAsync(reward_host + b, e->h_reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, cs));
     if (flags_host) MGYM_CUDA(cudaMemcpyAsync(flags_host + b, e->h_flags + b, cnt, cudaMemcpyDeviceToHost, cs));
