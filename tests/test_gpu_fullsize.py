@@ -121,3 +121,37 @@ def test_full_size_mountain_car_invariants(gym):
     assert not bool((out.flags & 2).any())                                           # :328 never truncates
     wall = (pos == np.float32(-1.2))
     assert bool((vel[wall] >= 0).all())                                              # :311-313
+
+
+def test_two_to_the_27_envs_on_one_gpu(gym, oracle):
+    """BASELINE configs[4]'s whole population (2^27 envs) on ONE handle: element offsets pass 2^31 and byte
+    offsets 2^33, so any 32-bit index arithmetic in the kernels would show here.  The first and the last 2048 envs
+    are replayed by the oracle (global indices key the Philox streams), for a fused rollout and for per-call steps."""
+    n, K, w = 1 << 27, 6, 2048
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 << 30:
+        pytest.skip("needs 24 GB of free device memory")
+    env = gym.GpuVecEnv(0, n, seed=77)
+    env.reset()
+    out = env.rollout(K)
+    for a in (0, n - w):
+        ref = oracle.VecState(0, w, auto_reset=1, seed=77, env_index_base=a)
+        ref.reset()
+        o, r, f, dc = ref.rollout(K)
+        assert_bit_equal(out.obs[:, :, a:a + w].cpu().numpy(), o, f"rollout obs of envs [{a},{a + w})")
+        assert_bit_equal(out.flags[:, a:a + w].cpu().numpy(), f, "rollout flags")
+        for t in range(3):
+            acts = env.sample_actions()
+            info = env.step(acts)
+            o1, r1, f1 = ref.step(acts[a:a + w].cpu().numpy())
+            assert_bit_equal(info.state[:, a:a + w].cpu().numpy(), o1, f"step obs of envs [{a},{a + w}) t={t}")
+            assert_bit_equal(info.flags[a:a + w].cpu().numpy(), f1, "step flags")
+        # the next window starts from the same point in time: rewind is not possible, so use a fresh handle
+        if a == 0:
+            env.close()
+            del out
+            torch.cuda.empty_cache()
+            env = gym.GpuVecEnv(0, n, seed=77)
+            env.reset()
+            out = env.rollout(K)
+    env.close()
