@@ -121,6 +121,10 @@ class GpuVecEnv:
             self.obs_is_state = self.kind in (CARTPOLE, MOUNTAIN_CAR, MOUNTAIN_CAR_CONTINUOUS)
             self._obs = self.state_view if self.obs_is_state else torch.empty((self.obs_dim, n), dtype=torch.float32,
                                                                               device=self.device)
+            # device pointers of the handle's own output buffers, marshalled once (a step is launch-bound for
+            # small batches: every microsecond of argument marshalling shows)
+            self._p_obs = None if self.obs_is_state else _ptr(self._obs)
+            self._p_reward, self._p_flags = _ptr(self._reward), _ptr(self._flags)
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
@@ -174,8 +178,8 @@ class GpuVecEnv:
         final = None
         if want_final_obs:
             final = torch.empty_like(self._obs)
-        _lib.check(self._lib.mgym_step(self._h, _ptr(actions), None if self.obs_is_state else _ptr(self._obs),
-                                       _ptr(self._reward), _ptr(self._flags), _ptr(final), self._stream()))
+        _lib.check(self._lib.mgym_step(self._h, _ptr(actions), self._p_obs, self._p_reward, self._p_flags, _ptr(final),
+                                       self._stream()))
         info = StepInfo(self._obs, self._reward, self._flags)
         return (info, final) if want_final_obs else info
 
