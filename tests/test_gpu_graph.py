@@ -107,3 +107,31 @@ def test_default_handle_still_refuses_capture_and_checkpoint_carries_the_clock(g
         assert same(acts, c.sample_actions())
         assert same(b.step(acts).state.clone(), c.step(acts).state)
     b.close(), c.close()
+
+
+@pytest.mark.parametrize("n", [4096, 1 << 20])  # one launch; eight pipelined chunk launches over two streams
+def test_step_host_with_a_device_clock(gym, n):
+    """mgym_step_host on a capturable handle: every chunk launch reads the step index from the device clock, which
+    one clock_advance_kernel moves on after the chunks have joined; results equal the default handle's."""
+    import numpy as np
+
+    a = gym.GpuVecEnv(0, n, seed=21)
+    b = gym.GpuVecEnv(0, n, seed=21, graph_capturable=True)
+    a.reset(), b.reset()
+    rng = np.random.default_rng(5)
+    bufs = []
+    for _ in range(2):
+        bufs.append((torch.empty((4, n)).pin_memory(), torch.empty(n).pin_memory(),
+                     torch.empty(n, dtype=torch.uint8).pin_memory()))
+    for t in range(30):
+        acts = torch.from_numpy(rng.integers(0, 2, n, dtype=np.uint8)).pin_memory()
+        a.step_host(acts, *bufs[0])
+        b.step_host(acts, *bufs[1])
+        for x, y in zip(bufs[0], bufs[1]):
+            assert same(x, y), f"host outputs differ at step {t}"
+        if t % 7 == 3:  # interleave device-buffer steps: both kinds of call advance the same clock
+            d = acts.cuda()
+            assert same(a.step(d).state, b.step(d).state)
+    assert a.step_index == b.step_index
+    assert a.stats() == b.stats()
+    a.close(), b.close()
