@@ -55,6 +55,8 @@ impl Builder {
     pub fn goal_velocity(mut self, v: f32) -> Self { self.cfg.goal_velocity = v; self }
     pub fn auto_reset(mut self, v: bool) -> Self { self.cfg.auto_reset = v as i32; self }
     pub fn validate_actions(mut self, v: bool) -> Self { self.cfg.validate_actions = v as i32; self }
+    pub fn track_stats(mut self, v: bool) -> Self { self.cfg.track_stats = v as i32; self }
+    pub fn track_returns(mut self, v: bool) -> Self { self.cfg.track_returns = v as i32; self }
     pub fn env_index_base(mut self, v: u64) -> Self { self.cfg.env_index_base = v; self }
     pub fn graph_capturable(mut self, v: bool) -> Self { self.cfg.device_clock = v as i32; self }
     pub fn build(self) -> Result<GpuVecEnv, MgymError> {

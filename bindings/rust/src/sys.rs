@@ -20,7 +20,7 @@ pub struct mgym_config {
     pub validate_actions: i32,
     pub env_index_base: u64,
     pub device_clock: i32, // 1 = CUDA-graph-capturable handle (step index + tile tickets on the device)
-    pub reserved0: i32,
+    pub track_returns: i32, // 1 = per-env running return for MountainCarContinuous / Pendulum statistics
 }
 
 #[repr(C)]

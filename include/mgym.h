@@ -45,7 +45,12 @@
  * Errors: every function returns 0 on success or a negative mgym_status; the message is
  * kept per thread (mgym_last_error).  Nothing aborts or throws across this boundary.  The
  * reference panics on an invalid action (assert!, cartpole.rs:252, mountain_car.rs:294);
- * here validate_actions=1 makes the next call on the handle return MGYM_ERR_INVALID_ACTION.
+ * here validate_actions=1 (a debug mode: one small pre-pass launch and a stream synchronisation per call)
+ * makes the offending mgym_step / mgym_rollout / mgym_step_host call itself return MGYM_ERR_INVALID_ACTION
+ * BEFORE anything is stepped: state, counters, statistics and step index are untouched, so the caller can
+ * correct the batch and retry, exactly as the reference asserts before any mutation.  Without it CartPole
+ * treats 0 as left and anything else as right (cartpole.rs:258-262) and MountainCar computes
+ * (a as f32) - 1.0 (mountain_car.rs:302).
  *
  * Threading: one handle = one GPU; calls on a handle must be serialised by the caller
  * (the reference's `&mut self`).  Different handles are independent.
@@ -97,15 +102,24 @@ typedef struct mgym_config {
   int32_t sutton_barto_reward; /* cartpole.rs:39, default 0 */
   int32_t is_euler;            /* cartpole.rs:40, default 1 */
   float goal_velocity;         /* mountain_car.rs:33, default 0.0 */
-  int32_t track_stats;         /* default 1: episode count / length / return sums (auto_reset only) */
+  int32_t track_stats;         /* default 1: episode count, terminated / truncated counts and length sum
+                                  (auto_reset only), and the return sum for the kinds whose return follows from
+                                  those (CartPole, MountainCar, Acrobot: constant rewards).  Costs no per-step
+                                  traffic: the episode length comes from a per-env START STAMP that a step only
+                                  reads (2 bytes, kinds with a time limit) or does not touch at all (no limit). */
   int32_t validate_actions;    /* default 0: debug mode, see Errors above */
   uint64_t env_index_base;     /* global index of this handle's env 0 (multi-GPU slices) */
   int32_t device_clock;        /* default 0.  1 = keep the step index and the tile-ticket base in device memory,
-                                  advanced by a one-thread kernel after every call: mgym_step, mgym_rollout and
+                                  advanced on the device by the last CTA of each launch (mgym_step_host's chunked
+                                  launches enqueue a one-thread kernel instead): mgym_step, mgym_rollout and
                                   mgym_sample_actions then carry no per-call launch parameter and may be captured
-                                  into a CUDA graph and replayed (same results as the eager calls).  Costs one
-                                  extra tiny launch per call; mgym_step_index then synchronises the device. */
-  int32_t reserved0;           /* 0 */
+                                  into a CUDA graph and replayed (same results as the eager calls).
+                                  mgym_step_index then synchronises the device. */
+  int32_t track_returns;       /* default 0.  1 = also accumulate the return sum of the kinds whose rewards are not
+                                  constants (MountainCarContinuous, Pendulum): a per-env running return, i.e. 4 bytes
+                                  read and 4 written per env-step in the per-call step kernel (free in mgym_rollout,
+                                  which keeps it in registers).  Needs track_stats.  Without it those kinds report
+                                  return_sum = 0. */
 } mgym_config;
 
 /* Episode statistics accumulated on the device since creation / mgym_stats_reset. */

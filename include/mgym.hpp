@@ -89,6 +89,9 @@ class GpuVecEnv {
     Builder& auto_reset(bool v) { cfg_.auto_reset = v; return *this; }
     Builder& max_episode_steps(int v) { cfg_.max_episode_steps = v; return *this; }
     Builder& validate_actions(bool v) { cfg_.validate_actions = v; return *this; }
+    Builder& track_stats(bool v) { cfg_.track_stats = v; return *this; }
+    // per-env running return, so that MountainCarContinuous / Pendulum statistics carry a return sum
+    Builder& track_returns(bool v) { cfg_.track_returns = v; return *this; }
     Builder& env_index_base(uint64_t v) { cfg_.env_index_base = v; return *this; }
     // step index and tile tickets on the device: step / rollout / sample_actions become CUDA-graph-capturable
     Builder& graph_capturable(bool v) { cfg_.device_clock = v; return *this; }

@@ -35,7 +35,7 @@ class Config(C.Structure):
         ("validate_actions", C.c_int32),
         ("env_index_base", C.c_uint64),
         ("device_clock", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("track_returns", C.c_int32),
     ]
 
 

@@ -7,11 +7,30 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <new>
 #include <string>
 
 #include "../../include/mgym.h"
 #include "mgym_kernels.cuh"
+
+// NCCL is resolved at run time (dlsym), so the library has no link dependency on it; the two enum values
+// mgym_stats_allreduce passes are taken from <nccl.h> where the header is installed and checked against the
+// values the header-less build assumes (NCCL has kept them since 2.0).
+#if defined(__has_include)
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define MGYM_HAVE_NCCL_H 1
+#endif
+#endif
+namespace {
+#ifdef MGYM_HAVE_NCCL_H
+constexpr int kNcclFloat64 = (int)ncclFloat64, kNcclSum = (int)ncclSum;
+static_assert(kNcclFloat64 == 8 && kNcclSum == 0, "NCCL enum values changed: update the header-less fallback below");
+#else
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (nccl.h 2.x)
+#endif
+}  // namespace
 
 using namespace mgym;
 
@@ -98,6 +117,9 @@ const char* const kNames[MGYM_NUM_KINDS] = {"CartPole-v1", "MountainCar-v0", "Mo
                                             "Pendulum-v1", "Acrobot-v1"};
 
 bool valid_kind(int kind) { return kind >= 0 && kind < MGYM_NUM_KINDS; }
+size_t counter_width(int cnt_mode) {
+  return cnt_mode == CNT_NONE ? 0 : ((cnt_mode == CNT_U16 || cnt_mode == CNT_S16) ? 2 : 4);
+}
 size_t action_size(int kind) { return kContinuous[kind] ? sizeof(float) : sizeof(uint8_t); }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -166,7 +188,6 @@ KernelParams base_params(const mgym_env* e) {
   p.reset_pool = e->pool_len ? e->reset_pool : nullptr;
   p.pool_len = e->pool_len;
   p.stats = (e->cfg.auto_reset && e->cfg.track_stats) ? e->stats : nullptr;
-  p.bad_action = e->cfg.validate_actions ? e->bad_action : nullptr;
   p.n = e->n;
   p.first = 0;
   p.ld = e->n;
@@ -191,15 +212,36 @@ int env_blocks_per_sm() {
 // Occupancy of a kernel is a per-device constant: query it once per (kernel instantiation, device).
 constexpr int kMaxDevices = 64;
 
-template <typename Kernel>
-int launch_persistent(Kernel kernel, const mgym_env* e, const KernelParams& p, uint64_t groups, cudaStream_t st) {
+// Every step_kernel / rollout_kernel instantiation has the same function-pointer TYPE, so the table is keyed by
+// the kernel's address (and the device), not by a template parameter.
+struct OccupancyCache {
+  static constexpr int kSlots = 256;
+  std::mutex mu;
+  const void* key[kSlots] = {};
+  int dev[kSlots] = {};
+  int per_sm[kSlots] = {};
+  int used = 0;
+  int find(const void* k, int d) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+      if (key[i] == k && dev[i] == d) return per_sm[i];
+    return 0;
+  }
+  void put(const void* k, int d, int v) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (used < kSlots) key[used] = k, dev[used] = d, per_sm[used] = v, ++used;
+  }
+};
+OccupancyCache g_occupancy;
+
+int launch_persistent(void (*kernel)(KernelParams), const mgym_env* e, const KernelParams& p, uint64_t groups,
+                      cudaStream_t st) {
   constexpr int threads = 256;
-  static int cached_per_sm[kMaxDevices] = {};  // one table per instantiation; benign if two threads race
-  int per_sm = e->device < kMaxDevices ? cached_per_sm[e->device] : 0;
+  int per_sm = g_occupancy.find(reinterpret_cast<const void*>(kernel), e->device);
   if (per_sm == 0) {
     MGYM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
     if (per_sm < 1) per_sm = 1;
-    if (e->device < kMaxDevices) cached_per_sm[e->device] = per_sm;
+    g_occupancy.put(reinterpret_cast<const void*>(kernel), e->device, per_sm);
   }
   if (env_blocks_per_sm() > 0) per_sm = env_blocks_per_sm();
   uint64_t blocks = (uint64_t)e->num_sms * per_sm;
@@ -274,7 +316,7 @@ bool use_tma() {
   return v;
 }
 
-// kind x vector width x auto/manual x counter width
+// kind x vector width x auto/manual x counter representation
 template <int KIND, int V, bool ROLLOUT>
 int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   const uint64_t groups = p.n / V;
@@ -283,13 +325,15 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
     // manual mode (the reference's protocol): counters are 32-bit, CartPole adds steps_beyond_terminated
     if (!autor && use_tma() && p.n % TMA_TILE == 0) return launch_step_tma<KIND, CNT_U32, false>(e, p, st);
     if (autor && use_tma() && p.n % TMA_TILE == 0) {
-      if constexpr (KIND == 0) {
-        return launch_step_tma<KIND, CNT_U16>(e, p, st);
+      if constexpr (KIND == 0) {  // CartPole always counts (500-step truncation, cartpole.rs:297)
+        if (e->cnt_mode == CNT_U16) return launch_step_tma<KIND, CNT_U16>(e, p, st);
+        return launch_step_tma<KIND, CNT_S16>(e, p, st);
       } else {
         switch (e->cnt_mode) {
           case CNT_NONE: return launch_step_tma<KIND, CNT_NONE>(e, p, st);
-          case CNT_U16: return launch_step_tma<KIND, CNT_U16>(e, p, st);
-          default: return launch_step_tma<KIND, CNT_U32>(e, p, st);
+          case CNT_S16: return launch_step_tma<KIND, CNT_S16>(e, p, st);
+          case CNT_S32_LAZY: return launch_step_tma<KIND, CNT_S32_LAZY>(e, p, st);
+          default: return launch_step_tma<KIND, CNT_S32>(e, p, st);
         }
       }
     }
@@ -305,9 +349,9 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
       return dispatch_mode<KIND, 4, false>(e, tail, st);
     }
   }
-  // rollout_kernel's FULL form: complete warp tiles, all three trajectory outputs, no action validation
+  // rollout_kernel's FULL form: complete warp tiles and all three trajectory outputs
   [[maybe_unused]] const bool full = ROLLOUT && V == 4 && autor && p.n % (32 * V) == 0 && p.obs_out && p.reward_out &&
-                                     p.flags_out && !p.bad_action;
+                                     p.flags_out;
 #define MGYM_LAUNCH(AUTO_, CNT_)                                                                         \
   do {                                                                                                   \
     if constexpr (ROLLOUT) {                                                                             \
@@ -321,12 +365,13 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
   } while (0)
   if (!autor) MGYM_LAUNCH(false, CNT_U32);
   if constexpr (KIND == 0) {
-    MGYM_LAUNCH(true, CNT_U16);
+    if (e->cnt_mode == CNT_U16) MGYM_LAUNCH(true, CNT_U16);
+    MGYM_LAUNCH(true, CNT_S16);
   } else {
-    switch (e->cnt_mode) {
+    switch (e->cnt_mode) {  // these kernels hold the count in registers: a lazy stamp is an ordinary one here
       case CNT_NONE: MGYM_LAUNCH(true, CNT_NONE);
-      case CNT_U16: MGYM_LAUNCH(true, CNT_U16);
-      default: MGYM_LAUNCH(true, CNT_U32);
+      case CNT_S16: MGYM_LAUNCH(true, CNT_S16);
+      default: MGYM_LAUNCH(true, CNT_S32);
     }
   }
 #undef MGYM_LAUNCH
@@ -350,22 +395,21 @@ int dispatch(const mgym_env* e, const KernelParams& p, bool vec4, cudaStream_t s
 
 template <int KIND>
 int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* mask, cudaStream_t st) {
-  if (mask && !p.obs_out && p.first == 0 && p.n % 16 == 0 && aligned16(mask)) {
-    const unsigned blocks = (unsigned)((p.n / 16 + 255) / 256);
-    switch (e->cnt_mode) {
-      case CNT_NONE: reset_sparse_kernel<KIND, CNT_NONE><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
-      case CNT_U16: reset_sparse_kernel<KIND, CNT_U16><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
-      default: reset_sparse_kernel<KIND, CNT_U32><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
-    }
-    MGYM_CUDA(cudaGetLastError());
-    return MGYM_OK;
-  }
-  const unsigned blocks = (unsigned)((p.n + 255) / 256);
+  const bool sparse = mask && !p.obs_out && p.first == 0 && p.n % 16 == 0 && aligned16(mask);
+  const unsigned blocks = sparse ? (unsigned)((p.n / 16 + 255) / 256) : (unsigned)((p.n + 255) / 256);
+#define MGYM_RESET(CNT_)                                                                        \
+  do {                                                                                          \
+    if (sparse) reset_sparse_kernel<KIND, CNT_><<<blocks, 256, 0, st>>>(p, mask, e->n_resets);  \
+    else reset_kernel<KIND, CNT_><<<blocks, 256, 0, st>>>(p, mask, e->n_resets);                \
+  } while (0)
   switch (e->cnt_mode) {
-    case CNT_NONE: reset_kernel<KIND, CNT_NONE><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
-    case CNT_U16: reset_kernel<KIND, CNT_U16><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
-    default: reset_kernel<KIND, CNT_U32><<<blocks, 256, 0, st>>>(p, mask, e->n_resets); break;
+    case CNT_NONE: MGYM_RESET(CNT_NONE); break;
+    case CNT_U16: MGYM_RESET(CNT_U16); break;
+    case CNT_U32: MGYM_RESET(CNT_U32); break;
+    case CNT_S16: MGYM_RESET(CNT_S16); break;
+    default: MGYM_RESET(CNT_S32); break;  // CNT_S32 and CNT_S32_LAZY share the representation
   }
+#undef MGYM_RESET
   MGYM_CUDA(cudaGetLastError());
   return MGYM_OK;
 }
@@ -386,7 +430,7 @@ bool is_capturing(cudaStream_t st) {
 int refuse_capture(const mgym_env* e, cudaStream_t st, const char* what, bool capturable) {
   if (!is_capturing(st)) return MGYM_OK;
   if (capturable && e->cfg.device_clock && e->cfg.validate_actions)
-    return fail(MGYM_ERR_BAD_ARGUMENT, "%s: validate_actions reads a flag back after every call, which a captured "
+    return fail(MGYM_ERR_BAD_ARGUMENT, "%s: validate_actions reads a flag back before every step, which a captured "
                 "stream cannot do; create the handle without it", what);
   if (capturable && e->cfg.device_clock) return MGYM_OK;
   if (capturable)
@@ -419,17 +463,28 @@ bool is_host_pointer(const void* ptr) {
   return attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost;
 }
 
-int check_bad_action(mgym_env* e, cudaStream_t st) {
-  if (!e->cfg.validate_actions) return MGYM_OK;
+int invalid_action(const mgym_env* e) {
+  return fail(MGYM_ERR_INVALID_ACTION,
+              "action outside Discrete(%d) (%s): the reference asserts action_space.contains; nothing was stepped",
+              kNumActions[e->kind], kNames[e->kind]);
+}
+
+// validate_actions (debug mode): the reference asserts BEFORE any mutation (cartpole.rs:252, mountain_car.rs:294),
+// so the batch is scanned by a pre-pass and an invalid one returns MGYM_ERR_INVALID_ACTION with the handle
+// untouched -- state, counters, statistics and step index are exactly as before the call.  Costs one small
+// launch and a stream synchronisation per call.  `count` device actions (Discrete kinds only).
+int validate_device_actions(mgym_env* e, const void* actions, uint64_t count, cudaStream_t st) {
+  if (!e->cfg.validate_actions || kContinuous[e->kind] || !actions) return MGYM_OK;
+  uint64_t blocks = (count + 255) / 256;
+  if (blocks > (uint64_t)e->num_sms * 8) blocks = (uint64_t)e->num_sms * 8;
+  MGYM_CUDA(cudaMemsetAsync(e->bad_action, 0, sizeof(uint32_t), st));
+  validate_actions_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const uint8_t*>(actions), count,
+                                                             (uint32_t)kNumActions[e->kind], e->bad_action);
+  MGYM_CUDA(cudaGetLastError());
   uint32_t bad = 0;
   MGYM_CUDA(cudaMemcpyAsync(&bad, e->bad_action, sizeof(bad), cudaMemcpyDeviceToHost, st));
   MGYM_CUDA(cudaStreamSynchronize(st));
-  if (bad) {
-    MGYM_CUDA(cudaMemsetAsync(e->bad_action, 0, sizeof(uint32_t), st));
-    return fail(MGYM_ERR_INVALID_ACTION, "action outside Discrete(%d) (%s): the reference asserts action_space.contains",
-                kNumActions[e->kind], kNames[e->kind]);
-  }
-  return MGYM_OK;
+  return bad ? invalid_action(e) : MGYM_OK;
 }
 
 }  // namespace
@@ -500,6 +555,7 @@ int mgym_config_default(int kind, mgym_config* cfg) {
   cfg->validate_actions = 0;
   cfg->env_index_base = 0;
   cfg->device_clock = 0;
+  cfg->track_returns = 0;
   switch (kind) {
     case MGYM_MOUNTAIN_CAR_CONTINUOUS_V0: cfg->max_episode_steps = 999; break;
     case MGYM_PENDULUM_V1: cfg->max_episode_steps = 200; break;
@@ -567,15 +623,20 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
   e->k = make_consts(kind, cfg);
   e->vec4 = (num_envs % 4 == 0) && (cfg.env_index_base % 4 == 0);
 
-  // counter representation (DESIGN.md "step counters")
+  // counter representation (CounterMode in mgym_kernels.cuh)
   if (!cfg.auto_reset) {
-    e->cnt_mode = CNT_U32;
+    e->cnt_mode = CNT_U32;  // the reference's steps_since_reset (cartpole.rs:24)
   } else if (kind == MGYM_CARTPOLE_V1) {
-    e->cnt_mode = CNT_U16;  // <= 500 between resets
+    // <= 500 between resets: a 16-bit start stamp (read-only per step); MGYM_CARTPOLE_COUNTER=u16 selects the
+    // round-1 read+write counter for A/B measurements
+    const char* s = getenv("MGYM_CARTPOLE_COUNTER");
+    e->cnt_mode = (s && strcmp(s, "u16") == 0) ? CNT_U16 : CNT_S16;
   } else if (cfg.max_episode_steps > 0 && cfg.max_episode_steps <= 65535) {
-    e->cnt_mode = CNT_U16;
-  } else if (cfg.max_episode_steps > 65535 || cfg.track_stats) {
-    e->cnt_mode = CNT_U32;
+    e->cnt_mode = CNT_S16;
+  } else if (cfg.max_episode_steps > 65535) {
+    e->cnt_mode = CNT_S32;
+  } else if (cfg.track_stats) {
+    e->cnt_mode = CNT_S32_LAZY;  // no time limit: only the statistics want the episode length
   } else {
     e->cnt_mode = CNT_NONE;  // MountainCar-v0 as in the reference: no counter at all
   }
@@ -588,10 +649,9 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
     const size_t n = (size_t)num_envs;
     MGYM_CUDA(cudaMalloc(&e->state, sizeof(float) * kStateDim[kind] * n));
     MGYM_CUDA(cudaMemset(e->state, 0, sizeof(float) * kStateDim[kind] * n));  // cartpole.rs:85 zero state
-    if (e->cnt_mode != CNT_NONE) {
-      const size_t w = e->cnt_mode == CNT_U16 ? 2 : 4;
-      MGYM_CUDA(cudaMalloc(&e->steps, w * n));
-      MGYM_CUDA(cudaMemset(e->steps, 0, w * n));
+    if (e->cnt_mode != CNT_NONE) {  // count 0, or start stamp 0 = the handle's step index right now
+      MGYM_CUDA(cudaMalloc(&e->steps, counter_width(e->cnt_mode) * n));
+      MGYM_CUDA(cudaMemset(e->steps, 0, counter_width(e->cnt_mode) * n));
     }
     if (!cfg.auto_reset && kind == MGYM_CARTPOLE_V1) {
       MGYM_CUDA(cudaMalloc(&e->sbt, sizeof(uint32_t) * n));
@@ -599,7 +659,7 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
       MGYM_CUDA(cudaGetLastError());
     }
     const bool analytic = kind == MGYM_CARTPOLE_V1 || kind == MGYM_MOUNTAIN_CAR_V0 || kind == MGYM_ACROBOT_V1;
-    if (cfg.auto_reset && cfg.track_stats && !analytic) {
+    if (cfg.auto_reset && cfg.track_stats && cfg.track_returns && !analytic) {
       MGYM_CUDA(cudaMalloc(&e->ep_return, sizeof(float) * n));
       MGYM_CUDA(cudaMemset(e->ep_return, 0, sizeof(float) * n));
     }
@@ -697,26 +757,26 @@ int mgym_set_state(mgym_env* e, const float* state, const uint32_t* steps, const
   const size_t n = (size_t)e->n;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   MGYM_CUDA(cudaMemcpyAsync(e->state, state, sizeof(float) * kStateDim[e->kind] * n, cudaMemcpyDefault, st));
-  if (e->cnt_mode == CNT_U32) {
-    if (steps) MGYM_CUDA(cudaMemcpyAsync(e->steps, steps, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
-    else MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint32_t) * n, st));
-  } else if (e->cnt_mode == CNT_U16) {
-    if (steps) {
-      const uint32_t* src = steps;
-      uint32_t* tmp = nullptr;
-      if (is_host_pointer(steps)) {  // set_state/get_state also accept host arrays
-        MGYM_CUDA(cudaMalloc(&tmp, sizeof(uint32_t) * n));
-        MGYM_CUDA(cudaMemcpyAsync(tmp, steps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-        src = tmp;
-      }
-      convert_kernel<uint32_t, uint16_t><<<blocks, 256, 0, st>>>(src, (uint16_t*)e->steps, n);
-      MGYM_CUDA(cudaGetLastError());
-      if (tmp) {
-        MGYM_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp);
-      }
-    } else {
-      MGYM_CUDA(cudaMemsetAsync(e->steps, 0, sizeof(uint16_t) * n, st));
+  if (e->cnt_mode != CNT_NONE) {
+    // the caller's uint32 counts -> this handle's representation (a count, or a start stamp relative to t)
+    const uint32_t* src = steps;
+    uint32_t* tmp = nullptr;
+    if (steps && is_host_pointer(steps)) {  // set_state/get_state also accept host arrays
+      MGYM_CUDA(cudaMalloc(&tmp, sizeof(uint32_t) * n));
+      MGYM_CUDA(cudaMemcpyAsync(tmp, steps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+      src = tmp;
+    }
+    const unsigned long long* td = e->cfg.device_clock ? e->clock : nullptr;
+    switch (e->cnt_mode) {
+      case CNT_U16: counters_from_steps_kernel<CNT_U16><<<blocks, 256, 0, st>>>(src, (uint16_t*)e->steps, n, e->t, td); break;
+      case CNT_U32: counters_from_steps_kernel<CNT_U32><<<blocks, 256, 0, st>>>(src, (uint32_t*)e->steps, n, e->t, td); break;
+      case CNT_S16: counters_from_steps_kernel<CNT_S16><<<blocks, 256, 0, st>>>(src, (uint16_t*)e->steps, n, e->t, td); break;
+      default: counters_from_steps_kernel<CNT_S32><<<blocks, 256, 0, st>>>(src, (uint32_t*)e->steps, n, e->t, td); break;
+    }
+    MGYM_CUDA(cudaGetLastError());
+    if (tmp) {
+      MGYM_CUDA(cudaStreamSynchronize(st));
+      cudaFree(tmp);
     }
   }
   if (e->sbt) {
@@ -735,20 +795,26 @@ int mgym_get_state(mgym_env* e, float* state, uint32_t* steps, uint32_t* sbt, vo
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (state) MGYM_CUDA(cudaMemcpyAsync(state, e->state, sizeof(float) * kStateDim[e->kind] * n, cudaMemcpyDefault, st));
   if (steps) {
-    if (e->cnt_mode == CNT_U32) {
-      MGYM_CUDA(cudaMemcpyAsync(steps, e->steps, sizeof(uint32_t) * n, cudaMemcpyDefault, st));
-    } else if (e->cnt_mode == CNT_U16) {
-      if (is_host_pointer(steps)) {
-        uint32_t* tmp = nullptr;
+    if (e->cnt_mode != CNT_NONE) {
+      const bool host = is_host_pointer(steps);
+      uint32_t* dst = steps;
+      uint32_t* tmp = nullptr;
+      if (host) {
         MGYM_CUDA(cudaMalloc(&tmp, sizeof(uint32_t) * n));
-        convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, tmp, n);
-        MGYM_CUDA(cudaGetLastError());
+        dst = tmp;
+      }
+      const unsigned long long* td = e->cfg.device_clock ? e->clock : nullptr;
+      switch (e->cnt_mode) {
+        case CNT_U16: steps_from_counters_kernel<CNT_U16><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, dst, n, e->t, td); break;
+        case CNT_U32: steps_from_counters_kernel<CNT_U32><<<blocks, 256, 0, st>>>((const uint32_t*)e->steps, dst, n, e->t, td); break;
+        case CNT_S16: steps_from_counters_kernel<CNT_S16><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, dst, n, e->t, td); break;
+        default: steps_from_counters_kernel<CNT_S32><<<blocks, 256, 0, st>>>((const uint32_t*)e->steps, dst, n, e->t, td); break;
+      }
+      MGYM_CUDA(cudaGetLastError());
+      if (host) {
         MGYM_CUDA(cudaMemcpyAsync(steps, tmp, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
         MGYM_CUDA(cudaStreamSynchronize(st));
         cudaFree(tmp);
-      } else {
-        convert_kernel<uint16_t, uint32_t><<<blocks, 256, 0, st>>>((const uint16_t*)e->steps, steps, n);
-        MGYM_CUDA(cudaGetLastError());
       }
     } else if (is_host_pointer(steps)) {
       memset(steps, 0, sizeof(uint32_t) * n);
@@ -784,16 +850,34 @@ int mgym_get_obs(mgym_env* e, float* obs_out, void* stream) {
 // checkpoint / resume
 // ---------------------------------------------------------------------------------------------
 namespace {
+// Everything a bit-identical continuation depends on besides the arrays themselves: a blob only loads into a handle
+// whose dynamics-relevant configuration matches (the seed, step index and reset index come from the blob).
 struct CheckpointHeader {
   uint32_t magic, version;
   int32_t kind, cnt_mode, auto_reset, has_sbt, has_ret;
-  uint64_t n, seed, t, n_resets;
+  int32_t is_euler, sutton_barto, max_episode_steps, track_stats;
+  float goal_velocity;
+  uint32_t pad0;
+  uint64_t n, seed, t, n_resets, env_index_base, pool_len;
 };
 constexpr uint32_t kCkptMagic = 0x4D47594Du;  // "MGYM"
+constexpr uint32_t kCkptVersion = 2;
 
-size_t counter_bytes(const mgym_env* e) {
-  return e->cnt_mode == CNT_NONE ? 0 : (e->cnt_mode == CNT_U16 ? 2 : 4) * (size_t)e->n;
+CheckpointHeader checkpoint_header(const mgym_env* e) {
+  CheckpointHeader h;
+  memset(&h, 0, sizeof(h));  // padding included: blobs are reproducible byte for byte
+  h.magic = kCkptMagic, h.version = kCkptVersion;
+  h.kind = e->kind, h.cnt_mode = e->cnt_mode, h.auto_reset = e->cfg.auto_reset;
+  h.has_sbt = e->sbt ? 1 : 0, h.has_ret = e->ep_return ? 1 : 0;
+  h.is_euler = e->cfg.is_euler, h.sutton_barto = e->cfg.sutton_barto_reward;
+  h.max_episode_steps = e->cfg.max_episode_steps, h.track_stats = e->cfg.track_stats;
+  h.goal_velocity = e->cfg.goal_velocity;
+  h.n = e->n, h.seed = e->seed, h.t = e->t, h.n_resets = e->n_resets;
+  h.env_index_base = e->cfg.env_index_base, h.pool_len = e->pool_len;
+  return h;
 }
+
+size_t counter_bytes(const mgym_env* e) { return counter_width(e->cnt_mode) * (size_t)e->n; }
 }  // namespace
 
 size_t mgym_checkpoint_size(const mgym_env* e) {
@@ -810,8 +894,7 @@ int mgym_checkpoint_save(mgym_env* e, void* blob, size_t blob_bytes, void* strea
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->n;
-  CheckpointHeader h{kCkptMagic, 1, e->kind, e->cnt_mode, e->cfg.auto_reset, e->sbt ? 1 : 0, e->ep_return ? 1 : 0,
-                     e->n,      e->seed, e->t, e->n_resets};
+  const CheckpointHeader h = checkpoint_header(e);
   uint8_t* out = static_cast<uint8_t*>(blob);
   memcpy(out, &h, sizeof(h));
   out += sizeof(h);
@@ -835,11 +918,24 @@ int mgym_checkpoint_load(mgym_env* e, const void* blob, size_t blob_bytes, void*
   if (blob_bytes < sizeof(CheckpointHeader)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: truncated blob");
   CheckpointHeader h;
   memcpy(&h, blob, sizeof(h));
-  if (h.magic != kCkptMagic || h.version != 1) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: not a checkpoint");
-  if (h.kind != e->kind || h.n != e->n || h.cnt_mode != e->cnt_mode || h.auto_reset != e->cfg.auto_reset ||
-      h.has_sbt != (e->sbt ? 1 : 0) || h.has_ret != (e->ep_return ? 1 : 0))
+  if (h.magic != kCkptMagic || h.version != kCkptVersion)
+    return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: not a checkpoint of this library version");
+  const CheckpointHeader mine = checkpoint_header(e);
+  if (h.kind != mine.kind || h.n != mine.n || h.cnt_mode != mine.cnt_mode || h.auto_reset != mine.auto_reset ||
+      h.has_sbt != mine.has_sbt || h.has_ret != mine.has_ret)
     return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: checkpoint of %s x %llu does not match this handle",
                 valid_kind(h.kind) ? kNames[h.kind] : "?", (unsigned long long)h.n);
+  if (h.is_euler != mine.is_euler || h.sutton_barto != mine.sutton_barto || h.max_episode_steps != mine.max_episode_steps ||
+      h.track_stats != mine.track_stats || memcmp(&h.goal_velocity, &mine.goal_velocity, sizeof(float)) != 0 ||
+      h.env_index_base != mine.env_index_base || h.pool_len != mine.pool_len)
+    return fail(MGYM_ERR_BAD_ARGUMENT,
+                "mgym_checkpoint_load: the checkpoint was taken with a different configuration (is_euler %d/%d, "
+                "sutton_barto %d/%d, max_episode_steps %d/%d, track_stats %d/%d, goal_velocity %g/%g, env_index_base "
+                "%llu/%llu, reset pool %llu/%llu): the continuation would not be bit-identical",
+                h.is_euler, mine.is_euler, h.sutton_barto, mine.sutton_barto, h.max_episode_steps, mine.max_episode_steps,
+                h.track_stats, mine.track_stats, (double)h.goal_velocity, (double)mine.goal_velocity,
+                (unsigned long long)h.env_index_base, (unsigned long long)mine.env_index_base,
+                (unsigned long long)h.pool_len, (unsigned long long)mine.pool_len);
   if (blob_bytes < mgym_checkpoint_size(e)) return fail(MGYM_ERR_BAD_ARGUMENT, "mgym_checkpoint_load: truncated blob");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -878,6 +974,7 @@ int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_ou
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = refuse_capture(e, st, "mgym_step", true)) return rc;
+  if (int rc = validate_device_actions(e, actions, e->n, st)) return rc;
   e->call_tickets = 0;
   KernelParams p = base_params(e);
   p.actions = actions;
@@ -892,8 +989,7 @@ int mgym_step(mgym_env* e, const void* actions, float* obs_out, float* reward_ou
                     aligned16(flags_out) && aligned16(final_obs_out);
   int rc = dispatch<false>(e, p, vec4, st);
   if (rc != MGYM_OK) return rc;
-  if ((rc = advance_clock(e, 1, st, /*fused=*/true)) != MGYM_OK) return rc;
-  return check_bad_action(e, st);
+  return advance_clock(e, 1, st, /*fused=*/true);
 }
 
 int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, float* reward_traj,
@@ -903,6 +999,7 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = refuse_capture(e, st, "mgym_rollout", true)) return rc;
+  if (int rc = validate_device_actions(e, actions, (uint64_t)K * e->n, st)) return rc;
   e->call_tickets = 0;
   KernelParams p = base_params(e);
   p.actions = actions;
@@ -922,8 +1019,7 @@ int mgym_rollout(mgym_env* e, uint32_t K, const void* actions, float* obs_traj, 
   MGYM_CUDA(cudaMemsetAsync(e->work + 3, 0, sizeof(unsigned long long), st));
   int rc = dispatch<true>(e, p, vec4, st);
   if (rc != MGYM_OK) return rc;
-  if ((rc = advance_clock(e, K, st, /*fused=*/true)) != MGYM_OK) return rc;
-  return check_bad_action(e, st);
+  return advance_clock(e, K, st, /*fused=*/true);
 }
 
 int mgym_sample_actions(mgym_env* e, void* actions_out, void* stream) {
@@ -956,6 +1052,12 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
   if (int rc = refuse_capture(e, st, "mgym_step_host", false)) return rc;
   e->call_tickets = 0;
   const size_t n = (size_t)e->n;
+  if (e->cfg.validate_actions && !kContinuous[e->kind]) {  // host actions: scanned on the host, before anything moves
+    const uint8_t* a = static_cast<const uint8_t*>(actions_host);
+    const uint8_t lim = (uint8_t)kNumActions[e->kind];
+    for (size_t i = 0; i < n; ++i)
+      if (a[i] >= lim) return invalid_action(e);
+  }
   const int od = kObsDim[e->kind];
   const size_t act = action_size(e->kind), asz = act * n, osz = sizeof(float) * od * n;
   const bool obs_is_state = kObsDim[e->kind] == kStateDim[e->kind];
@@ -1008,7 +1110,7 @@ int mgym_step_host(mgym_env* e, const void* actions_host, float* obs_host, float
   e->work_slot = 0;
   if (int rc = advance_clock(e, 1, st)) return rc;
   MGYM_CUDA(cudaStreamSynchronize(st));
-  return check_bad_action(e, st);
+  return MGYM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1060,7 +1162,6 @@ int mgym_stats_allreduce(mgym_env* e, void* nccl_comm, double* device_vec5_out, 
   int rc = mgym_stats_export(e, device_vec5_out, stream);
   if (rc != MGYM_OK) return rc;
   DeviceGuard guard(e->device);
-  constexpr int kNcclFloat64 = 8, kNcclSum = 0;
   const int nrc = fn(device_vec5_out, device_vec5_out, 5, kNcclFloat64, kNcclSum, nccl_comm, (cudaStream_t)stream);
   if (nrc != 0) return fail(MGYM_ERR_NCCL, "ncclAllReduce returned %d", nrc);
   return MGYM_OK;

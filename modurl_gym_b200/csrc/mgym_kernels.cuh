@@ -49,7 +49,21 @@ __device__ __forceinline__ void prefetch_global(const void* ptr) {
   }
 }
 
-enum CounterMode : int { CNT_NONE = 0, CNT_U16 = 1, CNT_U32 = 2 };
+// Per-env episode step count, as the handle keeps it between launches:
+//   CNT_NONE      nothing (no time limit, no statistics: MountainCar-v0 exactly as the reference, mountain_car.rs:10-23)
+//   CNT_U16/U32   the count itself, read AND written by every step (manual mode = the reference's steps_since_reset,
+//                 cartpole.rs:24; CNT_U16 is the round-1 CartPole form, kept for A/B measurements)
+//   CNT_S16/S32   a START STAMP: the handle's step index t at which the episode began (mod 2^16 / 2^32).  The count is
+//                 (t - stamp), so a step only READS the stamp; it is written when an episode ends (by the lane that
+//                 owns the finished env) -- 2 or 4 bytes read per env-step instead of a read and a write.
+//   CNT_S32_LAZY  the same stamp for kinds without a time limit, where only the statistics need the episode length:
+//                 not even read by a step unless the env finished (MountainCar-v0 with statistics: 22 B per env-step,
+//                 the SURVEY 8(d) contract figure, instead of 30).  Kernels that keep the count in registers anyway
+//                 (rollout, the LDG step form) treat it as CNT_S32.
+enum CounterMode : int { CNT_NONE = 0, CNT_U16 = 1, CNT_U32 = 2, CNT_S16 = 3, CNT_S32 = 4, CNT_S32_LAZY = 5 };
+__host__ __device__ constexpr bool cnt_is_stamp(int c) { return c >= CNT_S16; }
+__host__ __device__ constexpr bool cnt_is_lazy(int c) { return c == CNT_S32_LAZY; }
+__host__ __device__ constexpr bool cnt_staged(int c) { return c != CNT_NONE && c != CNT_S32_LAZY; }  // read by every step
 
 struct KernelParams {
   // resident env state (owned by the handle)
@@ -69,7 +83,6 @@ struct KernelParams {
   // statistics: u64 {episodes, terminated, truncated, length_sum}, then double return_sum
   unsigned long long* stats;
   unsigned long long* done_count;  // rollout: finished env-steps
-  uint32_t* bad_action;            // validate_actions: set to 1 on an out-of-range discrete action
   unsigned long long* work_counter;  // TMA step kernel: tile tickets (monotonic across launches)
   uint64_t work_base;                // first ticket of this launch
   // Device clock (handles created with device_clock = 1, the CUDA-graph-capturable mode): the step index and
@@ -440,6 +453,23 @@ template <>
 struct CounterType<CNT_U16> {
   using type = uint16_t;
 };
+template <>
+struct CounterType<CNT_S16> {
+  using type = uint16_t;
+};
+// stored value -> episode step count at the entry of step t, and back (t_next = the step index the count belongs to)
+template <int CNT>
+__device__ __forceinline__ uint32_t cnt_decode(typename CounterType<CNT>::type raw, uint64_t t) {
+  using cnt_t = typename CounterType<CNT>::type;
+  if constexpr (cnt_is_stamp(CNT)) return (uint32_t)(cnt_t)((uint32_t)t - (uint32_t)raw);
+  return raw;
+}
+template <int CNT>
+__device__ __forceinline__ typename CounterType<CNT>::type cnt_encode(uint32_t steps, uint64_t t_next) {
+  using cnt_t = typename CounterType<CNT>::type;
+  if constexpr (cnt_is_stamp(CNT)) return (cnt_t)((uint32_t)t_next - steps);
+  return (cnt_t)steps;
+}
 
 // =============================================================================================
 // Mode 1: per-call step kernel
@@ -450,6 +480,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD;
+  static_assert(!cnt_is_lazy(CNT) && (AUTO || !cnt_is_stamp(CNT)), "the host maps CNT_S32_LAZY to CNT_S32 here");
   StatAcc acc;
   const uint64_t groups = p.n / V;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -479,12 +510,9 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
         action[v] = a.v[v];
         g.steps[v] = 0;
         g.sbt[v] = SBT_NONE;
-        if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+        if constexpr (CNT != CNT_NONE) g.steps[v] = cnt_decode<CNT>(cnt.v[v], t_now);
         if constexpr (!AUTO && KIND == 0) g.sbt[v] = sb.v[v];
         g.ret[v] = track_ret ? er.v[v] : 0.0f;
-        if constexpr (!E::CONTINUOUS) {
-          if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
-        }
       }
     }
     if (want_final)
@@ -502,10 +530,13 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
       }
     }
     if constexpr (CNT != CNT_NONE) {
-      Vec<cnt_t, V> cnt;
+      // a start stamp only changes when an episode ended (the count of a finished env is 0 again by now)
+      if (!cnt_is_stamp(CNT) || packed_flags<KIND, V>(g) != 0u) {
+        Vec<cnt_t, V> cnt;
 #pragma unroll
-      for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
-      stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
+        for (int v = 0; v < V; ++v) cnt.v[v] = cnt_encode<CNT>(g.steps[v], t_now + 1);
+        stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
+      }
     }
     if constexpr (!AUTO && KIND == 0) {
       Vec<uint32_t, V> sb;
@@ -612,7 +643,7 @@ struct TmaLayout {
   static constexpr uint32_t OFF_ACT = E::SD * ROW;
   static constexpr uint32_t ACT_BYTES = TMA_TILE * sizeof(typename E::act_t);
   static constexpr uint32_t OFF_CNT = OFF_ACT + ACT_BYTES;
-  static constexpr uint32_t CNT_BYTES = CNT == CNT_NONE ? 0 : TMA_TILE * sizeof(typename CounterType<CNT>::type);
+  static constexpr uint32_t CNT_BYTES = cnt_staged(CNT) ? TMA_TILE * sizeof(typename CounterType<CNT>::type) : 0;
   static constexpr uint32_t OFF_RET = OFF_CNT + CNT_BYTES;
   static constexpr uint32_t RET_BYTES = (E::ANALYTIC_RETURN || !AUTO) ? 0 : ROW;
   // manual CartPole also carries steps_beyond_terminated (cartpole.rs:27)
@@ -651,6 +682,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   using act_t = typename E::act_t;
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD, V = 4;
+  static_assert(AUTO || !cnt_is_stamp(CNT), "manual mode keeps the reference's own counters");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
@@ -716,7 +748,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 #pragma unroll
         for (int c = 0; c < SD; ++c) tma::bulk_g2s(dst + c * L::ROW, p.state + (uint64_t)c * p.ld + e0, L::ROW, bar);
         tma::bulk_g2s(dst + L::OFF_ACT, actions + e0, L::ACT_BYTES, bar);
-        if constexpr (CNT != CNT_NONE)
+        if constexpr (cnt_staged(CNT))
           tma::bulk_g2s(dst + L::OFF_CNT, reinterpret_cast<const cnt_t*>(p.steps) + e0, L::CNT_BYTES, bar);
         if constexpr (!E::ANALYTIC_RETURN && AUTO) {
           if (track_ret) tma::bulk_g2s(dst + L::OFF_RET, p.ep_return + e0, L::ROW, bar);
@@ -790,7 +822,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         for (int c = 0; c < SD; ++c) row[c] = ldv<float, V>(reinterpret_cast<const float*>(st + c * L::ROW) + tid * V);
         const Vec<act_t, V> a = ldv<act_t, V>(reinterpret_cast<const act_t*>(st + L::OFF_ACT) + tid * V);
         Vec<cnt_t, V> cnt;
-        if constexpr (CNT != CNT_NONE) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + tid * V);
+        if constexpr (cnt_staged(CNT)) cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(st + L::OFF_CNT) + tid * V);
         Vec<float, V> er;
         if constexpr (!E::ANALYTIC_RETURN && AUTO) {
           if (track_ret) er = ldv<float, V>(reinterpret_cast<const float*>(st + L::OFF_RET) + tid * V);
@@ -804,13 +836,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
           action[v] = a.v[v];
           g.steps[v] = 0;
           g.sbt[v] = SBT_NONE;
-          if constexpr (CNT != CNT_NONE) g.steps[v] = cnt.v[v];
+          if constexpr (cnt_staged(CNT)) g.steps[v] = cnt_decode<CNT>(cnt.v[v], t_now);
           if constexpr (HAS_SBT) g.sbt[v] = sb.v[v];
           g.ret[v] = 0.0f;
           if constexpr (!E::ANALYTIC_RETURN && AUTO) g.ret[v] = track_ret ? er.v[v] : 0.0f;
-          if constexpr (!E::CONTINUOUS) {
-            if (p.bad_action && a.v[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
-          }
         }
       }
       __syncwarp();  // every lane of this warp has its values in registers
@@ -838,6 +867,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       // the memory-only experiment finishes nothing; in manual mode finished envs wait for the caller's reset
       const uint32_t fin = (MGYM_EXP_MEMONLY || !AUTO) ? 0u : fw;
       if (fin) {
+        if constexpr (cnt_is_lazy(CNT)) {
+          // the episode length is only needed now: the stamps of this lane's envs come straight from global memory
+          const Vec<cnt_t, V> sv = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
+#pragma unroll
+          for (int v = 0; v < V; ++v) g.steps[v] = cnt_decode<CNT>(sv.v[v], t_now) + 1u;
+        }
         tally_packed<KIND, V, true>(fin, g, acc);
         uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc((fin | (fin >> 1)) & 0x01010101u));
         uint16_t* items = q_items(qb);
@@ -849,6 +884,13 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
             g.ret[v] = 0.0f;
           }
         }
+        if constexpr (cnt_is_stamp(CNT)) {
+          // new start stamps for the finished envs (the others re-encode to the value they had)
+          Vec<cnt_t, V> sv;
+#pragma unroll
+          for (int v = 0; v < V; ++v) sv.v[v] = cnt_encode<CNT>(g.steps[v], t_now + 1);
+          stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, sv);
+        }
       }
 
 #pragma unroll
@@ -858,7 +900,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         for (int v = 0; v < V; ++v) o.v[v] = g.st[v][c];
         stv<float, V>(p.state + (uint64_t)c * p.ld + base, o);
       }
-      if constexpr (CNT != CNT_NONE) {
+      if constexpr (CNT != CNT_NONE && !cnt_is_stamp(CNT)) {
         Vec<cnt_t, V> cnt;
 #pragma unroll
         for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
@@ -933,6 +975,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD;
   static_assert(!FULL || (AUTO && V == 4), "the FULL form is built for the vector auto-reset path only");
+  static_assert(!cnt_is_lazy(CNT) && (AUTO || !cnt_is_stamp(CNT)), "the host maps CNT_S32_LAZY to CNT_S32 here");
   StatAcc acc;
   uint32_t dones = 0;  // finished env-steps of this lane's groups
   const uint64_t groups = p.n / V;
@@ -972,7 +1015,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
       if constexpr (CNT != CNT_NONE) {
         const Vec<cnt_t, V> cnt = ldv<cnt_t, V>(reinterpret_cast<const cnt_t*>(p.steps) + base);
 #pragma unroll
-        for (int v = 0; v < V; ++v) g.steps[v] = cnt.v[v];
+        for (int v = 0; v < V; ++v) g.steps[v] = cnt_decode<CNT>(cnt.v[v], t_first);
       }
       if constexpr (!AUTO && KIND == 0) {
         const Vec<uint32_t, V> sb = ldv<uint32_t, V>(p.sbt + base);
@@ -1051,14 +1094,6 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
 #pragma unroll
         for (int v = 0; v < V; ++v) action[v] = a_cur.get(v);
       }
-      if constexpr (!E::CONTINUOUS && !FULL) {
-        if (p.bad_action) {
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (action[v] >= E::NUM_ACTIONS) *p.bad_action = 1u;
-        }
-      }
-
       step_group<KIND, V, AUTO, false, false, RESET_BY_CALLER, TRUSTED, true>(p, active, base, t, action, track_ret, g,
                                                                               acc);
 
@@ -1164,7 +1199,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
       if constexpr (CNT != CNT_NONE) {
         Vec<cnt_t, V> cnt;
 #pragma unroll
-        for (int v = 0; v < V; ++v) cnt.v[v] = (cnt_t)g.steps[v];
+        for (int v = 0; v < V; ++v) cnt.v[v] = cnt_encode<CNT>(g.steps[v], t_first + p.K);
         stv<cnt_t, V>(reinterpret_cast<cnt_t*>(p.steps) + base, cnt);
       }
       if constexpr (!AUTO && KIND == 0) {
@@ -1205,7 +1240,7 @@ __device__ __forceinline__ void reset_one(const KernelParams& p, uint64_t i, uin
   }
 #pragma unroll
   for (int c = 0; c < E::SD; ++c) p.state[(uint64_t)c * p.ld + i] = st[c];
-  if constexpr (CNT != CNT_NONE) reinterpret_cast<cnt_t*>(p.steps)[i] = 0;  // cartpole.rs:243
+  if constexpr (CNT != CNT_NONE) reinterpret_cast<cnt_t*>(p.steps)[i] = cnt_encode<CNT>(0u, launch_t(p));  // cartpole.rs:243
   if (p.sbt) p.sbt[i] = SBT_NONE;                                            // cartpole.rs:239
   if (p.ep_return) p.ep_return[i] = 0.0f;
   if (p.obs_out) {
@@ -1300,10 +1335,29 @@ __global__ void sample_actions_kernel(typename Env<KIND>::act_t* out, uint64_t n
   out[i] = action_from_word<KIND>(ws[g & 3]);
 }
 
-template <typename From, typename To>
-__global__ void convert_kernel(const From* in, To* out, uint64_t n) {
+// episode step counts (uint32, what mgym_set_state / mgym_get_state exchange) <-> the handle's own representation
+template <int CNT>
+__global__ void counters_from_steps_kernel(const uint32_t* steps_or_null, typename CounterType<CNT>::type* out, uint64_t n,
+                                           uint64_t t, const unsigned long long* t_dev) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (To)in[i];
+  if (t_dev) t = *t_dev;
+  if (i < n) out[i] = cnt_encode<CNT>(steps_or_null ? steps_or_null[i] : 0u, t);
+}
+template <int CNT>
+__global__ void steps_from_counters_kernel(const typename CounterType<CNT>::type* in, uint32_t* steps, uint64_t n,
+                                           uint64_t t, const unsigned long long* t_dev) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_dev) t = *t_dev;
+  if (i < n) steps[i] = cnt_decode<CNT>(in[i], t);
+}
+
+// validate_actions: is every discrete action inside Discrete(num_actions)?  Runs BEFORE the step, so an invalid
+// batch leaves the handle untouched (the reference asserts before any mutation, cartpole.rs:252)
+__global__ void validate_actions_kernel(const uint8_t* actions, uint64_t count, uint32_t num_actions, uint32_t* bad) {
+  bool mine = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    mine |= actions[i] >= num_actions;
+  if (__any_sync(0xffffffffu, mine) && (threadIdx.x & 31) == 0) *bad = 1u;
 }
 
 __global__ void fill_u32_kernel(uint32_t* out, uint32_t value, uint64_t n) {

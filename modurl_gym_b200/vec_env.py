@@ -77,7 +77,7 @@ class GpuVecEnv:
 
     def __init__(self, kind, num_envs, device=0, seed=0, auto_reset=True, max_episode_steps=None,
                  sutton_barto_reward=False, is_euler=True, goal_velocity=0.0, track_stats=True,
-                 validate_actions=False, env_index_base=0, graph_capturable=False):
+                 validate_actions=False, env_index_base=0, graph_capturable=False, track_returns=False):
         self._lib = _lib.load()
         self.kind = KINDS[kind] if isinstance(kind, str) else int(kind)
         if isinstance(device, torch.device):
@@ -94,6 +94,9 @@ class GpuVecEnv:
         cfg.goal_velocity = float(goal_velocity)
         cfg.track_stats = int(bool(track_stats))
         cfg.validate_actions = int(bool(validate_actions))
+        # per-env running return: gives MountainCarContinuous / Pendulum statistics a return sum (8 more bytes per
+        # env-step in the per-call step kernel; free in rollouts)
+        cfg.track_returns = int(bool(track_returns))
         cfg.env_index_base = int(env_index_base)
         # device_clock: step index and tile tickets live on the device, so step / rollout / sample_actions can be
         # captured into a CUDA graph (torch.cuda.graph) and replayed; one extra one-thread launch per call
@@ -303,6 +306,13 @@ class GpuVecEnv:
         from .distributed import all_reduce_stats_vector
 
         return EpisodeStats(*all_reduce_stats_vector(self.stats_tensor(), group))
+
+    def all_reduce_stats_native(self, comm):
+        """The same sum through the C ABI's own collective: mgym_stats_allreduce on a raw ncclComm_t
+        (`comm`: distributed.NativeNcclComm).  Returns the reduced 5-double device vector."""
+        out = torch.empty(5, dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.mgym_stats_allreduce(self._h, comm.handle, _ptr(out), self._stream()))
+        return out
 
 
 def _hptr(a):

@@ -189,16 +189,20 @@ def test_cartpole_single_env_trace_1e4(gym, oracle):
     got_steps[:] = host(stp_all)[:, 0].view(np.uint32)
     # ... against the oracle
     n_done = 0
+    want_obs, want_rew = np.zeros_like(got_obs), np.zeros_like(got_rew)
     for t in range(T):
         o, r, f = ref.step(actions[t:t + 1])
         assert got_flg[t] == f[0], f"flags differ at step {t}"
         assert got_steps[t] == ref.steps[0], f"step counter differs at step {t}"
         assert_bit_equal(got_obs[t], o[:, 0], f"obs at step {t}")
         assert got_rew[t] == r[0]
+        want_obs[t], want_rew[t] = o[:, 0], r[0]
         n_done += int(f[0] != 0)
     assert n_done > 300  # random policy: ~22 steps per episode
-    rel = np.max(np.abs(got_obs - got_obs) / np.maximum(np.abs(got_obs), 1e-30))
+    # north_star's stated bar (1e-6 relative over the 10^4-step trace), on top of the bit equality above
+    rel = np.max(np.abs(got_obs - want_obs) / np.maximum(np.abs(want_obs), 1e-30))
     assert rel <= REL_TOL[0]
+    assert np.max(np.abs(got_rew - want_rew)) <= REL_TOL[0]
     s = env.stats()
     assert s.episodes == n_done == ref.stats.episodes and s.length_sum == ref.stats.length_sum
     env.close()
@@ -209,7 +213,7 @@ def test_cartpole_single_env_trace_1e4(gym, oracle):
 # ---------------------------------------------------------------------------------------------
 def run_auto_parity(gym, oracle, kind, n, T, seed, use_pool=False, want_final=False, **cfg):
     rng = np.random.default_rng(1000 + kind)
-    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=seed, **cfg)
+    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=seed, track_returns=True, **cfg)
     ocfg = {k: v for k, v in cfg.items() if k in ("max_episode_steps", "sutton_barto_reward", "is_euler",
                                                     "goal_velocity", "env_index_base")}
     ocfg = {k: (int(v) if k != "goal_velocity" else v) for k, v in ocfg.items()}
@@ -365,7 +369,7 @@ def test_mountain_car_wall_and_goal(gym, oracle):
 def test_rollout_parity(gym, oracle, kind, n, policy):
     K = {0: 300, 1: 200, 2: 200, 3: 210, 4: 120}[kind]
     rng = np.random.default_rng(70 + kind)
-    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=0xABCDEF)
+    env = gym.GpuVecEnv(kind, n, auto_reset=True, seed=0xABCDEF, track_returns=True)
     ref = oracle.VecState(kind, n, auto_reset=1, seed=0xABCDEF)
     env.reset(), ref.reset()
     for chunk in range(2):  # two consecutive rollouts: the step index carries over
@@ -424,8 +428,17 @@ def test_invalid_action_is_reported(gym):
         a = torch.zeros(8, dtype=torch.uint8, device="cuda")
         env.step(a)
         a[5] = bad
+        before, t_before = [x.clone() for x in env.get_state()], env.step_index
         with pytest.raises(gym.InvalidActionError):
             env.step(a)
+        with pytest.raises(gym.InvalidActionError):
+            env.rollout(3, a.repeat(3, 1))
+        with pytest.raises(gym.InvalidActionError):
+            env.step_host(a.cpu(), None, None, None)
+        # the reference asserts before any mutation (cartpole.rs:252): nothing was stepped
+        assert env.step_index == t_before
+        for x, y in zip(before, env.get_state()):
+            assert torch.equal(x.view(torch.int32), y.view(torch.int32))
         env.step(torch.zeros(8, dtype=torch.uint8, device="cuda"))  # the handle stays usable
     env = gym.GpuVecEnv(0, 8)
     with pytest.raises(TypeError):

@@ -49,7 +49,7 @@ def test_random_session_matches_oracle(gym, oracle, session):
         cfg["env_index_base"] = int(rng.choice([4, 4096, 1 << 33]))
     seed = int(rng.integers(0, 1 << 40))
     ocfg = {k: (int(v) if k != "goal_velocity" else v) for k, v in cfg.items()}
-    env = gym.GpuVecEnv(kind, n, auto_reset=auto, seed=seed, **cfg)
+    env = gym.GpuVecEnv(kind, n, auto_reset=auto, seed=seed, track_returns=True, **cfg)
     ref = oracle.VecState(kind, n, auto_reset=int(auto), seed=seed, **ocfg)
     what = f"session {session}: {KIND_NAMES[kind]} n={n} auto={auto} {cfg}"
     assert_bit_equal(host(env.reset()), ref.reset(), what + " reset")
