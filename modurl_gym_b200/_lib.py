@@ -93,6 +93,7 @@ PROBES = {
     "mgym_probe_trig_checksum": (_i, [C.c_uint32, _u64, C.c_uint32, _vp]),
     "mgym_probe_fast_exhaustive": (_i, [_i, _u64, _u64, _vp]),
     "mgym_probe_fast_div_random": (_i, [_u64, _u64, _vp]),
+    "mgym_probe_cartpole_fast": (_i, [_u64, _u64, _vp]),
 }
 
 _lib = None

@@ -1207,6 +1207,21 @@ int mgym_probe_fast_div_random(uint64_t seed, uint64_t n, uint64_t* out2) {
   return MGYM_OK;
 }
 
+int mgym_probe_cartpole_fast(uint64_t seed, uint64_t n, uint64_t* out3) {
+  unsigned long long* d = nullptr;
+  MGYM_CUDA(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  MGYM_CUDA(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+  mgym_config cfg;
+  mgym_config_default(MGYM_CARTPOLE_V1, &cfg);
+  cartpole_fast_random_kernel<<<148 * 8, 256>>>(seed, n, make_consts(MGYM_CARTPOLE_V1, cfg), d);
+  MGYM_CUDA(cudaGetLastError());
+  unsigned long long h[3];
+  MGYM_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  out3[0] = h[0], out3[1] = h[1], out3[2] = h[2];
+  return MGYM_OK;
+}
+
 int mgym_probe_trig_checksum(uint32_t first, uint64_t count, uint32_t stride, uint64_t* out) {
   unsigned long long* d = nullptr;
   MGYM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));

@@ -358,6 +358,14 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
   float aux[V];
   bool ok[V];
   bool all_ok = true;
+  // the fast forms write the state unconditionally; the (rare) env whose precondition failed is restored from
+  // here and redone with the reference form
+  float old[V][E::SD];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int c = 0; c < E::SD; ++c) old[v][c] = g.st[v][c];
+  }
   if constexpr (TRUSTED && E::HAS_TRUSTED) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -405,8 +413,13 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
   }
   if (!all_ok) {
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (!ok[v]) E::dynamics(g.st[v], action[v], p.k, aux[v]);
+    for (int v = 0; v < V; ++v) {
+      if (!ok[v]) {
+#pragma unroll
+        for (int c = 0; c < E::SD; ++c) g.st[v][c] = old[v][c];
+        E::dynamics(g.st[v], action[v], p.k, aux[v]);
+      }
+    }
   }
   uint32_t pending = 0;
 #pragma unroll
@@ -1455,6 +1468,56 @@ __global__ void fast_div_random_kernel(uint64_t seed, uint64_t n, unsigned long 
   }
   atomicAdd(checked, my_checked);
   if (my_bad) atomicAdd(bad, my_bad);
+}
+
+// CartPole's fast forms (scalar and packed pair) vs the reference form on random states drawn ACROSS the fast
+// precondition (|theta| < 0.25, |theta_dot| < 10): whenever a fast form says ok its state must be the reference's
+// bits, and inside the precondition it must say ok (the numerators are then provably div_safe, see Env<0>::fast_ok).
+// out = {checked, bad, accepted}
+__global__ void cartpole_fast_random_kernel(uint64_t seed, uint64_t n, EnvConsts k, unsigned long long* out) {
+  unsigned long long my_checked = 0, my_bad = 0, my_ok = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    float st[2][4];
+    uint8_t act[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 w = philox_env(seed, 2 * i + j, 0, 9u);
+      // theta: uniform in (-0.3, 0.3), every 8th sample a raw bit pattern below 0.25 (tiny values, denormals);
+      // theta_dot: uniform in (-12, 12); x, x_dot: wide
+      const float u0 = (w.x >> 8) * 0x1p-24f, u1 = (w.y >> 8) * 0x1p-24f, u2 = (w.z >> 8) * 0x1p-24f, u3 = (w.w >> 8) * 0x1p-24f;
+      st[j][0] = (u0 - 0.5f) * 6.0f;
+      st[j][1] = (u1 - 0.5f) * 20.0f;
+      st[j][2] = ((w.x & 7u) == 0u) ? __uint_as_float((w.z % 0x3e800000u) | (w.y << 31)) : (u2 - 0.5f) * 0.6f;
+      st[j][3] = (u3 - 0.5f) * 24.0f;
+      act[j] = (uint8_t)(w.w & 1u);
+    }
+    float ref[2][4], one[2][4], two[2][4], aux = 0.0f;
+    bool ok1[2], ok2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ref[j][c] = one[j][c] = two[j][c] = st[j][c];
+      Env<0>::dynamics(ref[j], act[j], k, aux);
+      ok1[j] = Env<0>::dynamics_fast(one[j], act[j], k, aux);
+    }
+    Env<0>::dynamics_fast2(two[0], two[1], act[0], act[1], k, ok2[0], ok2[1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const bool inside = fabsf(st[j][2]) < 0.25f && fabsf(st[j][3]) < 10.0f;
+      bool bad = inside != ok1[j] || inside != ok2[j];
+      if (ok1[j] && ok2[j]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          bad |= __float_as_uint(one[j][c]) != __float_as_uint(ref[j][c]) || __float_as_uint(two[j][c]) != __float_as_uint(ref[j][c]);
+      }
+      my_checked += 1;
+      my_bad += bad ? 1 : 0;
+      my_ok += ok1[j] ? 1 : 0;
+    }
+  }
+  atomicAdd(out, my_checked);
+  if (my_bad) atomicAdd(out + 1, my_bad);
+  atomicAdd(out + 2, my_ok);
 }
 
 // digest of (x, sin x, cos x) from sincos_ref over magnitudes first, first+stride, ... and both signs: the same

@@ -60,3 +60,29 @@ def random_states(rng, kind, n):
         s[2] = rng.uniform(-12, 12, n)
         s[3] = rng.uniform(-28, 28, n)
     return s
+
+
+# ---- 10^4-step teacher-forced traces of the kinds the reference lacks (tests/golden/make_f64_traces.py) ----------
+F64_TRACES = {2: "mountain_car_continuous", 3: "pendulum", 4: "acrobot"}
+F64_TOL = 1e-5  # north_star: "within 1e-5 for Acrobot/Pendulum" -- relative, with an absolute floor of the same size
+
+
+def load_f64_trace(kind):
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"f64_trace_{F64_TRACES[kind]}.npz")
+    return dict(np.load(path))
+
+
+def check_f64_trace(kind, tr, obs, reward, flags):
+    """obs [OD, T], reward [T], flags [T] of ONE step taken from every recorded (state, count, action) of the trace,
+    against the float64 answers: |got - want| <= 1e-5 * max(1, |want|); flags exact except on marked seams."""
+    want_obs, want_rew = tr["obs"].astype(np.float64).T, tr["reward"].astype(np.float64)
+    ok = tr["seam"] == 0
+    err_obs = np.abs(obs.astype(np.float64) - want_obs) / np.maximum(1.0, np.abs(want_obs))
+    err_rew = np.abs(reward.astype(np.float64) - want_rew) / np.maximum(1.0, np.abs(want_rew))
+    want_flags = (tr["terminated"] | (tr["truncated"] << 1)).astype(np.uint8)
+    assert err_obs[:, ok].max() <= F64_TOL, (KIND_NAMES[kind], "obs", float(err_obs[:, ok].max()))
+    assert err_rew[ok].max() <= F64_TOL, (KIND_NAMES[kind], "reward", float(err_rew[ok].max()))
+    assert np.array_equal(flags[ok], want_flags[ok]), (KIND_NAMES[kind], "flags", int((flags[ok] != want_flags[ok]).sum()))
+    return float(err_obs[:, ok].max()), float(err_rew[ok].max())

@@ -51,3 +51,14 @@ def test_fdiv_fast_random_pairs(lib):
     out = (C.c_uint64 * 2)()
     assert lib.mgym_probe_fast_div_random(0xD1CE, 1 << 28, out) == 0
     assert out[0] > (1 << 28) and out[1] == 0, f"fdiv_fast: {out[1]} of {out[0]} pairs differ"
+
+
+def test_cartpole_fast_forms_on_random_states(lib):
+    """Env<0>::fast_ok (|theta| < 0.25, |theta_dot| < 10) is a SUFFICIENT precondition: on 2^28 random states drawn
+    across its boundary the scalar and the packed-pair fast forms accept exactly the states inside it, and every
+    accepted state steps to the reference form's bits (cartpole.rs:253-290 operator order)."""
+    out = (C.c_uint64 * 3)()
+    assert lib.mgym_probe_cartpole_fast(0xCA47, 1 << 27, out) == 0
+    checked, bad, accepted = out[0], out[1], out[2]
+    assert checked == 1 << 28 and bad == 0, f"CartPole fast forms: {bad} of {checked} states differ"
+    assert 0.55 * checked < accepted < 0.85 * checked, accepted  # both sides of the precondition were exercised
