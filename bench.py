@@ -98,7 +98,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] legs (headline only)")
     ap.add_argument("--only-configs", default="", help="comma-separated sub-config names (default: all)")
-    ap.add_argument("--config-seconds", type=float, default=0.4, help="timed region per sub-config")
+    ap.add_argument("--config-seconds", type=float, default=0.2, help="one timed window of a sub-config (3 are taken)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every sub-config (smoke runs on small GPUs)")
     return ap.parse_args()
 
@@ -309,8 +309,11 @@ class Ctx:
         clocks = self.sampler.window(w0, w1) if (self.rank == 0 and self.sampler) else None
         return sec, clocks
 
-    def calibrated(self, fn, seconds, min_reps=2, max_reps=100000):
-        """warm-up (>= 3 calls), then a timed region of about `seconds`."""
+    def calibrated(self, fn, seconds, windows=3, idle=0.25, min_reps=2, max_reps=100000):
+        """warm-up (>= 3 calls), then `windows` timed regions of about `seconds` each with `idle` seconds of rest
+        before each (the chip's power governor clocks a hot kernel down within milliseconds, and how far depends on
+        what ran just before: every window starts from the same rested state).  Returns the BEST window (time, reps,
+        its own clock record) and the per-window times -- the same best-of-N convention as MEASURED_PEAKS.json."""
         torch = self.torch
         for _ in range(3):
             fn()
@@ -322,8 +325,15 @@ class Ctx:
         torch.cuda.synchronize()
         one = self.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 1e-6))
         reps = int(min(max_reps, max(min_reps, round(seconds / one))))
-        sec, clocks = self.timed(fn, reps)
-        return sec, reps, clocks
+        best, all_sec = None, []
+        for _ in range(windows):
+            time.sleep(idle)
+            fn()  # one untimed call: the first launch after an idle gap pays the clock ramp
+            sec, clocks = self.timed(fn, reps)
+            all_sec.append(sec)
+            if best is None or sec < best[0]:
+                best = (sec, clocks)
+        return best[0], reps, best[1], all_sec
 
 
 def make_actions(torch, env, kind, shape, device, gen):
@@ -378,7 +388,7 @@ def run_subconfig(ctx, m, spec, args, peak):
         contract = ROLLOUT_CONTRACT[kind]
         what = (f"fused rollout, {steps_per_pass} steps per pass as {K}-step launches over one reused "
                 f"[{K}][..][N] trajectory ring, actions read from a [{K}][N] ring")
-    sec, reps, clocks = ctx.calibrated(one_pass, args.config_seconds)
+    sec, reps, clocks, windows = ctx.calibrated(one_pass, args.config_seconds)
     env_steps = float(n) * ctx.world * steps_per_pass * reps
     rate = env_steps / sec
     per_gpu_gbs = contract * (rate / ctx.world) / 1e9
@@ -390,6 +400,7 @@ def run_subconfig(ctx, m, spec, args, peak):
         "env_steps_per_s": rate, "bytes_per_env_step_contract": contract,
         "achieved_GBps_per_gpu": per_gpu_gbs, "peak_GBps": peak, "frac": per_gpu_gbs / peak,
         "mean_episode_length": stats.length_sum / max(stats.episodes, 1), "clocks": clocks,
+        "window_ms_per_pass": [1e3 * w / reps for w in windows], "timing": "best of the windows listed",
     }
     env.close()
     del env
@@ -420,7 +431,7 @@ def run_mixed_suite(ctx, m, args, native_comm):
             env.rollout(K, None, obs=o, reward=r, flags=f, count_done=False)
             count[0] += 1
 
-    sec, reps, clocks = ctx.calibrated(sweep, args.config_seconds)
+    sec, reps, clocks, windows = ctx.calibrated(sweep, args.config_seconds)
     launches = count[0]
     steps = K * reps
     # the collective (off the per-step path): one all-reduce of the 5 x 5 statistics matrix
@@ -455,6 +466,7 @@ def run_mixed_suite(ctx, m, args, native_comm):
         "per_kind": rows,
         "collective": "one all-reduce (sum) of a 5x5 float64 statistics matrix after the timed region",
         "allreduce_ms": allreduce_ms, "native_nccl_allreduce": native, "clocks": clocks,
+        "window_ms_per_sweep": [1e3 * w / reps for w in windows], "timing": "best of the windows listed",
     }
     for env in envs:
         env.close()

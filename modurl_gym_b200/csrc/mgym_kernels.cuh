@@ -31,22 +31,27 @@
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
 
-#ifndef MGYM_ACT_PF_DIST
-#define MGYM_ACT_PF_DIST 4
-#endif
-#ifndef MGYM_ACT_PF_LEVEL
-#define MGYM_ACT_PF_LEVEL 1
+#ifndef MGYM_ACT_RING
+#define MGYM_ACT_RING 8  // rollout: steps of action look-ahead staged in shared memory (power of two)
 #endif
 
 namespace mgym {
 
-template <int LEVEL>
-__device__ __forceinline__ void prefetch_global(const void* ptr) {
-  if constexpr (LEVEL == 1) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+// cp.async (LDGSTS): global -> shared without passing through registers; completion is tracked per thread in
+// commit groups.  BYTES = 4 (uint8 x 4 actions) or 16 (float x 4).
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t smem_dst, const void* gsrc) {
+  static_assert(BYTES == 4 || BYTES == 16, "one lane's four actions");
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
   } else {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
   }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 }
 
 // Per-env episode step count, as the handle keeps it between launches:
@@ -166,6 +171,16 @@ template <typename T, int V>
 struct RawActions {
   Vec<T, V> v;
   __device__ __forceinline__ void load(const T* p) { v = ldv<T, V>(p); }
+  __device__ __forceinline__ void load_shared(uint32_t addr) {
+    static_assert(sizeof(T) * V == 16 || V == 1, "one 128-bit shared load");
+    if constexpr (V == 1) {
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(*reinterpret_cast<uint32_t*>(&v.v[0])) : "r"(addr));
+    } else {
+      uint4 u;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+      *reinterpret_cast<uint4*>(&v) = u;
+    }
+  }
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int i = 0; i < V; ++i) v.v[i] = T(0);
@@ -176,6 +191,7 @@ template <>
 struct RawActions<uint8_t, 4> {
   uint32_t w;
   __device__ __forceinline__ void load(const uint8_t* p) { w = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ void load_shared(uint32_t addr) { asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr)); }
   __device__ __forceinline__ void zero() { w = 0; }
   __device__ __forceinline__ uint8_t get(int i) const { return (uint8_t)(w >> (8 * i)); }
 };
@@ -356,26 +372,19 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
                                            Group<KIND, V>& g, StatAcc& acc) {
   using E = Env<KIND>;
   float aux[V];
-  bool ok[V];
-  bool all_ok = true;
-  // the fast forms write the state unconditionally; the (rare) env whose precondition failed is restored from
-  // here and redone with the reference form
-  float old[V][E::SD];
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-#pragma unroll
-    for (int c = 0; c < E::SD; ++c) old[v][c] = g.st[v][c];
-  }
-  if constexpr (TRUSTED && E::HAS_TRUSTED) {
+  for (int v = 0; v < V; ++v) aux[v] = 0.0f;
+  if constexpr (E::HAS_BATCH) {
+    // Acrobot: the RK4 stages test their own intermediates, so the fast form runs first (it writes the state
+    // unconditionally) and an env whose test failed is restored from here and redone with the reference form
+    bool ok[V];
+    bool all_ok = true;
+    float old[V][E::SD];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      aux[v] = 0.0f;
-      ok[v] = true;
-      E::dynamics_trusted(g.st[v], action[v], p.k);
-    }
-  } else if constexpr (E::HAS_BATCH) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) aux[v] = 0.0f;
+      for (int c = 0; c < E::SD; ++c) old[v][c] = g.st[v][c];
+    }
     if constexpr (BATCH_PAIRS && V == 4) {
       // two batches of two: half the loop body (Acrobot's rolled RK4 loop then stalls less on instruction
       // fetch) for half the instruction-level parallelism.  Measured: +7 % in the per-call step kernel,
@@ -392,33 +401,47 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) all_ok = all_ok && ok[v];
-  } else if constexpr (E::HAS_PAIR && V % 2 == 0) {
+    if (!all_ok) {
 #pragma unroll
-    for (int v = 0; v < V; v += 2) {
-      aux[v] = aux[v + 1] = 0.0f;
-      E::dynamics_fast2(g.st[v], g.st[v + 1], action[v], action[v + 1], p.k, ok[v], ok[v + 1]);
-      all_ok = all_ok && ok[v] && ok[v + 1];
+      for (int v = 0; v < V; ++v) {
+        if (!ok[v]) {
+#pragma unroll
+          for (int c = 0; c < E::SD; ++c) g.st[v][c] = old[v][c];
+          E::dynamics(g.st[v], action[v], p.k, aux[v]);
+        }
+      }
     }
   } else {
+    // The precondition of the fast forms is a function of the inputs: test it first.  A lane that holds an env
+    // outside it (rare: states nobody reaches by stepping) runs the reference form for all its envs -- the two
+    // forms agree bit for bit wherever the fast one applies, so results do not depend on the path taken.
+    bool all_ok = true;
+    if constexpr (!(TRUSTED && E::HAS_TRUSTED)) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      aux[v] = 0.0f;
-      if constexpr (OBS_VALID && E::HAS_OBS_CACHE) {
-        ok[v] = E::dynamics_fast_cached(g.st[v], action[v], p.k, aux[v], g.obs[v]);
-      } else {
-        ok[v] = E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
-      }
-      all_ok = all_ok && ok[v];
+      for (int v = 0; v < V; ++v) all_ok = all_ok & E::fast_ok(g.st[v], action[v], p.k);
     }
-  }
-  if (!all_ok) {
+    if (all_ok) {
+      if constexpr (E::HAS_GROUP) {
+        E::template dynamics_fast_group<V>(g.st, action, p.k);
+      } else if constexpr (E::HAS_PAIR && V % 2 == 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (!ok[v]) {
+        for (int v = 0; v < V; v += 2) {
+          bool oka, okb;
+          E::dynamics_fast2(g.st[v], g.st[v + 1], action[v], action[v + 1], p.k, oka, okb);
+        }
+      } else {
 #pragma unroll
-        for (int c = 0; c < E::SD; ++c) g.st[v][c] = old[v][c];
-        E::dynamics(g.st[v], action[v], p.k, aux[v]);
+        for (int v = 0; v < V; ++v) {
+          if constexpr (OBS_VALID && E::HAS_OBS_CACHE) {
+            E::dynamics_fast_cached(g.st[v], action[v], p.k, aux[v], g.obs[v]);
+          } else {
+            E::dynamics_fast(g.st[v], action[v], p.k, aux[v]);
+          }
+        }
       }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) E::dynamics(g.st[v], action[v], p.k, aux[v]);
     }
   }
   uint32_t pending = 0;
@@ -989,6 +1012,10 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   constexpr int SD = E::SD, OD = E::OD;
   static_assert(!FULL || (AUTO && V == 4), "the FULL form is built for the vector auto-reset path only");
   static_assert(!cnt_is_lazy(CNT) && (AUTO || !cnt_is_stamp(CNT)), "the host maps CNT_S32_LAZY to CNT_S32 here");
+  constexpr int ACT_RING = MGYM_ACT_RING;
+  static_assert((ACT_RING & (ACT_RING - 1)) == 0, "power of two");
+  constexpr uint32_t RING_STRIDE = 256 * V * sizeof(act_t);  // one row of the CTA: 256 threads x V actions
+  __shared__ __align__(16) act_t act_ring[V == 4 ? ACT_RING : 1][256 * V];
   StatAcc acc;
   uint32_t dones = 0;  // finished env-steps of this lane's groups
   const uint64_t groups = p.n / V;
@@ -1042,17 +1069,31 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
       }
     }
 
-    // Actions ping-pong between two registers (sets): the row of step k+1 is loaded into the one that step k
-    // does not read, so the load stays in flight for a whole step and no loop-carried copy exists that the
-    // compiler could hoist next to the load (it did: 34 % of all stall samples sat on that one move).
     if constexpr (E::HAS_OBS_CACHE) {  // step_group<OBS_VALID> relies on g.obs from here on
 #pragma unroll
       for (int v = 0; v < V; ++v) E::obs(g.st[v], g.obs[v]);
     }
-    RawActions<act_t, V> a0, a1;
-    a0.zero();
-    a1.zero();
-    if (!policy && active) a0.load(actions + base);
+    // Actions are staged MGYM_ACT_RING steps ahead in shared memory with cp.async: every lane copies its own
+    // 4 (uint8) or 16 (float) bytes of the row ACT_RING steps ahead and later reads back exactly those bytes, so no
+    // cross-lane synchronisation is needed, only its own commit groups.  A load issued one step ahead into a
+    // register (round 1, plus an L1 prefetch four rows ahead) arrived late under the write-heavy DRAM traffic of a
+    // rollout: 10-25 % of all stall samples sat on the first use of the action word (profiles/README.md).
+    constexpr bool STAGED = V == 4;  // scalar lanes (ragged sizes) load the row at its use
+    [[maybe_unused]] uint32_t ring_addr = 0;
+    const act_t* act_ptr = actions ? actions + base : nullptr;  // row being fetched next
+    if constexpr (STAGED) {
+      ring_addr = tma::smem_u32(&act_ring[0][threadIdx.x * V]);
+      if (!policy) {
+#pragma unroll
+        for (int j = 0; j < ACT_RING; ++j) {
+          if (active && (uint32_t)j < p.K) {
+            cp_async<sizeof(act_t) * V>(ring_addr + j * RING_STRIDE, act_ptr);
+            act_ptr += p.ld;
+          }
+          cp_async_commit();  // one group per row, empty or not: the wait below counts groups
+        }
+      }
+    }
 
     // Sum of the lengths of the episodes an env finishes during this launch = steps_before + K - steps_after,
     // so the per-step tally is not needed here (counters saturate only after 4e9 steps).
@@ -1068,19 +1109,26 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     float* obs_ptr = (FULL || p.obs_out) ? p.obs_out + base : nullptr;
     float* rew_ptr = (FULL || p.reward_out) ? p.reward_out + base : nullptr;
     uint8_t* flg_ptr = (FULL || p.flags_out) ? p.flags_out + base : nullptr;
-    const act_t* act_ptr = actions ? actions + base + p.ld : nullptr;  // next step's row
 
     // One step of this warp tile.  `trusted_tag` selects the form without per-step precondition tests; the
     // return value says whether the invariant behind it still holds (it can only break when a reset state
     // comes from an injected pool, and is re-checked right there, under the same rare branch).
-    // loads the action row of step `row` (if there is one) and pulls the row MGYM_ACT_PF_DIST steps further
-    // towards the SM, so that the load itself hits L1/L2 rather than DRAM
-    auto load_row = [&](RawActions<act_t, V>& dst, uint32_t row) {
-      if (!policy && active && row < p.K) {
-#if MGYM_ACT_PF_DIST > 0
-        if (row + MGYM_ACT_PF_DIST < p.K) prefetch_global<MGYM_ACT_PF_LEVEL>(act_ptr + (uint64_t)MGYM_ACT_PF_DIST * p.ld);
-#endif
-        dst.load(act_ptr);
+    // the actions of step `row`: out of the ring (and the row ACT_RING steps later starts on its way into the slot
+    // just read), or straight from global memory for scalar lanes
+    auto fetch_row = [&](RawActions<act_t, V>& dst, uint32_t row) {
+      dst.zero();
+      if (policy) return;
+      if constexpr (STAGED) {
+        cp_async_wait<ACT_RING - 1>();  // all but the ACT_RING - 1 newest groups have landed: row `row` is here
+        const uint32_t slot = ring_addr + (row & (ACT_RING - 1)) * RING_STRIDE;
+        if (active) dst.load_shared(slot);
+        if (active && row + ACT_RING < p.K) {
+          cp_async<sizeof(act_t) * V>(slot, act_ptr);
+          act_ptr += p.ld;
+        }
+        cp_async_commit();
+      } else {
+        if (active) dst.load(act_ptr);
         act_ptr += p.ld;
       }
     };
@@ -1185,12 +1233,14 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
       }
       one_step(std::false_type{}, kk, a_cur);
     };
-    for (uint32_t kk = 0; kk < p.K; kk += 2) {
-      load_row(a1, kk + 1);
-      step_any(kk, a0);
-      if (kk + 1 >= p.K) break;
-      load_row(a0, kk + 2);
-      step_any(kk + 1, a1);
+#pragma unroll 1
+    for (uint32_t kk = 0; kk < p.K; ++kk) {
+      RawActions<act_t, V> a_cur;
+      fetch_row(a_cur, kk);
+      step_any(kk, a_cur);
+    }
+    if constexpr (STAGED) {
+      if (!policy) cp_async_wait<0>();  // the ring is reused by this warp's next tile
     }
     if constexpr (kLenIdentity) {
       if (active) {
