@@ -362,6 +362,25 @@ __device__ __forceinline__ bool group_trusted(const Group<KIND, V>& g) {
   return mine;
 }
 
+// The cold path of step_group: the reference form for every env of a lane that holds one outside the fast forms'
+// precondition.  Out of line on purpose: inlined, its long sinf/cosf/fmodf reductions sit in the middle of the hot
+// function and the register allocator pays for them on the hot path (Pendulum's step: +14 % instructions, mostly
+// re-loaded constants); as a call it costs the hot path nothing.
+// Arguments and results travel BY VALUE in one struct: a reference to the caller's own state array would make that
+// array live in local memory on the hot path too.
+template <int KIND, int V>
+struct LaneIO {
+  float st[V][Env<KIND>::SD];
+  float aux[V];
+  typename Env<KIND>::act_t action[V];
+};
+template <int KIND, int V>
+__device__ __noinline__ LaneIO<KIND, V> dynamics_reference_lane(LaneIO<KIND, V> io, const EnvConsts& k) {
+#pragma unroll 1
+  for (int v = 0; v < V; ++v) Env<KIND>::dynamics(io.st[v], io.action[v], k, io.aux[v]);
+  return io;
+}
+
 // TRUSTED (kinds with Env::HAS_TRUSTED): the caller has established Env::trusted_entry for every slot, which the
 // dynamics themselves then preserve, so the fast form runs without its per-step precondition test.
 // OBS_VALID (kinds with Env::HAS_OBS_CACHE): g.obs is the observation of the state in g.st on entry.
@@ -419,6 +438,7 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
     if constexpr (!(TRUSTED && E::HAS_TRUSTED)) {
 #pragma unroll
       for (int v = 0; v < V; ++v) all_ok = all_ok & E::fast_ok(g.st[v], action[v], p.k);
+      all_ok = all_ok & E::fast_enabled(p.k);
     }
     if (all_ok) {
       if constexpr (E::HAS_GROUP) {
@@ -440,8 +460,21 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
         }
       }
     } else {
+      LaneIO<KIND, V> io;
 #pragma unroll
-      for (int v = 0; v < V; ++v) E::dynamics(g.st[v], action[v], p.k, aux[v]);
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int c = 0; c < E::SD; ++c) io.st[v][c] = g.st[v][c];
+        io.aux[v] = 0.0f;
+        io.action[v] = action[v];
+      }
+      io = dynamics_reference_lane<KIND, V>(io, p.k);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int c = 0; c < E::SD; ++c) g.st[v][c] = io.st[v][c];
+        aux[v] = io.aux[v];
+      }
     }
   }
   uint32_t pending = 0;
@@ -450,9 +483,9 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
     if constexpr (AUTO) g.sbt[v] = SBT_NONE;  // auto-reset presumes reset() precedes every episode
     if constexpr (E::OUTCOME_FROM_OBS) {
       E::obs(g.st[v], g.obs[v]);
-      g.flags[v] = E::outcome_obs(g.st[v], g.obs[v], g.steps[v], p.k, g.reward[v]);
+      g.flags[v] = E::template outcome_obs<!AUTO>(g.st[v], g.obs[v], g.steps[v], p.k, g.reward[v]);
     } else {
-      g.flags[v] = E::outcome(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
+      g.flags[v] = E::template outcome<!AUTO>(g.st[v], action[v], aux[v], g.steps[v], g.sbt[v], p.k, g.reward[v]);
     }
     if (track_ret) g.ret[v] = fadd(g.ret[v], g.reward[v]);
     if constexpr (!E::OBS_IS_STATE || WANT_FINAL) {
