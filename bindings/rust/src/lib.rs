@@ -74,6 +74,12 @@ pub struct VecStepInfo {
     pub flags: *const u8,
 }
 
+/// Host-side actions of one step: Discrete kinds take bytes, Box kinds (MountainCarContinuous, Pendulum) floats.
+pub enum HostActions<'a> {
+    Discrete(&'a [u8]),
+    Box(&'a [f32]),
+}
+
 pub struct GpuVecEnv {
     h: *mut sys::mgym_env,
     kind: Kind,
@@ -109,13 +115,34 @@ impl GpuVecEnv {
         check(unsafe { sys::mgym_rollout(self.h, k, actions, obs_traj, reward_traj, flags_traj, done_count, self.stream) })
     }
     /// Host-buffer step for scalar adapters and tests: H2D actions, step, D2H results, synchronises.
-    pub fn step_host(&mut self, actions: &[u8], obs: &mut [f32], reward: &mut [f32], flags: &mut [u8]) -> Result<(), MgymError> {
-        assert_eq!(actions.len() as u64, self.num_envs);
-        check(unsafe { sys::mgym_step_host(self.h, actions.as_ptr() as *const c_void, obs.as_mut_ptr(),
-                                           reward.as_mut_ptr(), flags.as_mut_ptr(), self.stream) })
+    /// Every slice length is checked against what the C side reads or writes (N actions of the kind's own type,
+    /// obs_dim * N observations, N rewards, N flags), so this safe function cannot reach out of bounds.
+    pub fn step_host(&mut self, actions: HostActions<'_>, obs: &mut [f32], reward: &mut [f32], flags: &mut [u8])
+                     -> Result<(), MgymError> {
+        let n = self.num_envs as usize;
+        let continuous = unsafe { sys::mgym_action_is_continuous(self.kind as i32) } == 1;
+        let act_ptr = match actions {
+            HostActions::Discrete(a) => {
+                assert!(!continuous, "this kind takes Box (f32) actions");
+                assert_eq!(a.len(), n, "actions: one u8 per env");
+                a.as_ptr() as *const c_void
+            }
+            HostActions::Box(a) => {
+                assert!(continuous, "this kind takes Discrete (u8) actions");
+                assert_eq!(a.len(), n, "actions: one f32 per env");
+                a.as_ptr() as *const c_void
+            }
+        };
+        assert_eq!(obs.len(), self.obs_dim() * n, "obs: obs_dim * N floats, component-major");
+        assert_eq!(reward.len(), n, "reward: N floats");
+        assert_eq!(flags.len(), n, "flags: N bytes");
+        check(unsafe { sys::mgym_step_host(self.h, act_ptr, obs.as_mut_ptr(), reward.as_mut_ptr(), flags.as_mut_ptr(),
+                                           self.stream) })
     }
-    /// Testable::set_state (cartpole.rs:444-446); host or device pointers.
+    /// Testable::set_state (cartpole.rs:444-446) from a HOST array of state_dim * N floats, component-major.
     pub fn set_state(&mut self, state_soa: &[f32]) -> Result<(), MgymError> {
+        let sd = unsafe { sys::mgym_state_dim(self.kind as i32) } as usize;
+        assert_eq!(state_soa.len(), sd * self.num_envs as usize, "state: state_dim * N floats");
         check(unsafe { sys::mgym_set_state(self.h, state_soa.as_ptr(), ptr::null(), ptr::null(), self.stream) })
     }
     pub fn stats(&mut self) -> Result<sys::mgym_stats, MgymError> {

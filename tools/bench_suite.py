@@ -19,12 +19,14 @@ import torch  # noqa: E402
 
 import modurl_gym_b200 as m  # noqa: E402
 
-NAMES = ["CartPole-v1", "MountainCar-v0", "MountainCarContinuous-v0", "Pendulum-v1", "Acrobot-v1"]
+import bench  # noqa: E402  (the repo-root bench.py: one table of contract bytes for both tools)
+
+NAMES = bench.NAMES
 DEFAULT_N = [1 << 24, 1 << 24, 1 << 24, 1 << 22, 1 << 22]
-# algorithmic bytes per env-step; counters as this build keeps them
-STEP_BYTES = [42, 8 + 8 + 1 + 4 + 1 + 8, 8 + 8 + 4 + 4 + 1 + 4 + 8, 8 + 8 + 12 + 4 + 4 + 1 + 4 + 8, 16 + 16 + 24 + 1 + 4 + 1 + 4]
-OBS_BYTES = [16, 8, 8, 12, 24]
-ACT_BYTES = [1, 1, 4, 4, 1]
+# SURVEY 8(d) contract bytes per env-step (what bench.py quotes fractions against)
+STEP_BYTES = bench.STEP_CONTRACT
+OBS_BYTES = bench.OBS_BYTES
+ACT_BYTES = bench.ACT_BYTES
 
 
 def peak():

@@ -17,3 +17,5 @@ tools/ncu_export.sh prof_step_tma_pendulum_$R step_kernel_tma 3 -- $S --kinds 3 
 tools/ncu_export.sh prof_rollout_pendulum_$R rollout_kernel 3 -- $S --kinds 3 --modes rollout > /dev/null
 tools/ncu_export.sh prof_step_tma_acrobot_$R step_kernel_tma 3 -- $S --kinds 4 --modes step > /dev/null
 ls gpurun_out | grep $R | head -60
+python tools/bench_suite.py --modes step,rollout,rollout_policy,manual > gpurun_out/suite_$R.jsonl 2> gpurun_out/suite_$R.err
+python tools/small_batch_latency.py > gpurun_out/small_batch_$R.md 2>&1
