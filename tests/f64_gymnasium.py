@@ -1,7 +1,8 @@
-"""Float64 transcriptions of the three Gymnasium classic-control envs the reference does NOT implement
-(`/root/reference/src/classic_control.rs:1-2` declares only cartpole and mountain_car): MountainCarContinuous-v0,
-Pendulum-v1 and Acrobot-v1, written from Gymnasium's published equations, independently of oracle/mgym_oracle.c
-and of the CUDA code.  Plain Python/numpy float64, one env, no batching.
+"""Float64 transcriptions of the five classic-control envs, independent of oracle/mgym_oracle.c and of the CUDA code:
+MountainCarContinuous-v0, Pendulum-v1 and Acrobot-v1 -- which the reference does NOT implement
+(`/root/reference/src/classic_control.rs:1-2` declares only cartpole and mountain_car) -- from Gymnasium's published
+equations, and CartPole-v1 / MountainCar-v0 from the reference's own (`cartpole.rs:251-348`,
+`mountain_car.rs:293-330`).  Plain Python/numpy float64, one env, no batching.
 
 TEST INFRASTRUCTURE: this is the yardstick the f32 oracle and the device path are measured against for the kinds
 whose parity is otherwise unpinned.  It is not an implementation of the product path.
@@ -13,10 +14,64 @@ import math
 
 import numpy as np
 
-MOUNTAIN_CAR_CONTINUOUS, PENDULUM, ACROBOT = 2, 3, 4
-TIME_LIMIT = {MOUNTAIN_CAR_CONTINUOUS: 999, PENDULUM: 200, ACROBOT: 500}
-STATE_DIM = {MOUNTAIN_CAR_CONTINUOUS: 2, PENDULUM: 2, ACROBOT: 4}
-OBS_DIM = {MOUNTAIN_CAR_CONTINUOUS: 2, PENDULUM: 3, ACROBOT: 6}
+CARTPOLE, MOUNTAIN_CAR, MOUNTAIN_CAR_CONTINUOUS, PENDULUM, ACROBOT = 0, 1, 2, 3, 4
+# CartPole's 500 is the reference's own early return (cartpole.rs:296-306); MountainCar-v0 never truncates in the
+# reference (mountain_car.rs:328); the other three are Gymnasium's TimeLimit wrappers
+TIME_LIMIT = {CARTPOLE: 500, MOUNTAIN_CAR: 0, MOUNTAIN_CAR_CONTINUOUS: 999, PENDULUM: 200, ACROBOT: 500}
+STATE_DIM = {CARTPOLE: 4, MOUNTAIN_CAR: 2, MOUNTAIN_CAR_CONTINUOUS: 2, PENDULUM: 2, ACROBOT: 4}
+OBS_DIM = {CARTPOLE: 4, MOUNTAIN_CAR: 2, MOUNTAIN_CAR_CONTINUOUS: 2, PENDULUM: 3, ACROBOT: 6}
+
+
+# ---- CartPole-v1 and MountainCar-v0: the two kinds the reference DOES implement, transcribed a third time (after
+# ---- oracle/mgym_oracle.c and the CUDA code) in float64, from the reference's equations, so that long traces reach
+# ---- what its 100-step fixtures do not: the 500-step truncation, the wall and the goal ------------------------------
+def cartpole_step(state, action, count):
+    """/root/reference/src/classic_control/cartpole.rs:251-348, Euler integrator, default rewards, first step after
+    reset() (steps_beyond_terminated = None).  -> (next_state, obs, reward, terminated, truncated, seam)"""
+    gravity, masscart, masspole, length, force_mag, tau = 9.8, 1.0, 0.1, 0.5, 10.0, 0.02
+    total_mass, polemass_length = masspole + masscart, masspole * length
+    theta_threshold, x_threshold = 12 * 2 * math.pi / 360, 2.4
+    x, x_dot, theta, theta_dot = (float(v) for v in state)
+    force = force_mag if int(action) == 1 else -force_mag                                  # :258-262
+    costheta, sintheta = math.cos(theta), math.sin(theta)                                  # :264-265
+    temp = (force + polemass_length * theta_dot * theta_dot * sintheta) / total_mass       # :267-268
+    thetaacc = (gravity * sintheta - costheta * temp) / (
+        length * (4.0 / 3.0 - masspole * costheta * costheta / total_mass))                # :269-270
+    xacc = temp - polemass_length * thetaacc * costheta / total_mass                       # :271
+    x, x_dot = x + tau * x_dot, x_dot + tau * xacc                                         # :274-275
+    theta, theta_dot = theta + tau * theta_dot, theta_dot + tau * thetaacc                 # :276-277
+    terminated = bool(x < -x_threshold or x > x_threshold or theta < -theta_threshold or theta > theta_threshold)
+    seam = min(abs(abs(x) - x_threshold), abs(abs(theta) - theta_threshold)) < 1e-6
+    nxt = np.array([x, x_dot, theta, theta_dot])
+    if count + 1 >= 500:  # :296-306: the early return -- truncated, NOT done, reward 1, whatever the pole did
+        return nxt, nxt.copy(), 1.0, False, True, False
+    return nxt, nxt.copy(), 1.0, terminated, False, seam                                    # :310-329
+
+
+def cartpole_reset(rng):
+    return rng.uniform(-0.05, 0.05, size=4)                                                # :240
+
+
+def mountain_car_step(state, action, goal_velocity=0.0):
+    """/root/reference/src/classic_control/mountain_car.rs:293-330"""
+    min_position, max_position, max_speed, goal_position, force, gravity = -1.2, 0.6, 0.07, 0.5, 0.001, 0.0025
+    position, velocity = float(state[0]), float(state[1])
+    velocity += (int(action) - 1) * force + math.cos(3 * position) * (-gravity)            # :301-302
+    seam = abs(abs(velocity) - max_speed) < 1e-8
+    velocity = min(max(velocity, -max_speed), max_speed)                                   # :304
+    position += velocity                                                                   # :306
+    seam = seam or abs(position - min_position) < 1e-6 or abs(position - max_position) < 1e-6
+    position = min(max(position, min_position), max_position)                              # :308
+    if position == min_position and velocity < 0:                                          # :311-313
+        velocity = 0.0
+    terminated = bool(position >= goal_position and velocity >= goal_velocity)             # :318
+    seam = seam or abs(position - goal_position) < 1e-6
+    nxt = np.array([position, velocity])
+    return nxt, nxt.copy(), -1.0, terminated, seam                                          # :319, :328
+
+
+def mountain_car_reset(rng):
+    return np.array([rng.uniform(-0.6, -0.4), 0.0])                                        # :281-285
 
 
 # ---- MountainCarContinuous-v0 (gymnasium/envs/classic_control/continuous_mountain_car.py) -------------------------
@@ -127,13 +182,23 @@ def acrobot_reset(rng):
     return rng.uniform(-0.1, 0.1, size=4)
 
 
-STEP = {MOUNTAIN_CAR_CONTINUOUS: mountain_car_continuous_step, PENDULUM: pendulum_step, ACROBOT: acrobot_step}
-RESET = {MOUNTAIN_CAR_CONTINUOUS: mountain_car_continuous_reset, PENDULUM: pendulum_reset, ACROBOT: acrobot_reset}
+STEP = {MOUNTAIN_CAR: mountain_car_step, MOUNTAIN_CAR_CONTINUOUS: mountain_car_continuous_step, PENDULUM: pendulum_step,
+        ACROBOT: acrobot_step}
+RESET = {CARTPOLE: cartpole_reset, MOUNTAIN_CAR: mountain_car_reset, MOUNTAIN_CAR_CONTINUOUS: mountain_car_continuous_reset,
+         PENDULUM: pendulum_reset, ACROBOT: acrobot_reset}
 
 
 def policy(kind, rng, state, episode):
     """Actions that reach every branch: uniform random ones (beyond the Box bounds, to exercise the clamps) and, on
     every other episode, an energy-pumping rule that actually gets the car to the goal / the acrobot above the bar."""
+    if kind == CARTPOLE:  # a PD rule that balances for the full 500 steps, or coin flips (falls within ~20 steps)
+        if episode % 2 == 0:
+            return int(state[2] + 0.5 * state[3] + 0.05 * state[0] + 0.1 * state[1] > 0)
+        return int(rng.integers(0, 2))
+    if kind == MOUNTAIN_CAR:  # push with the velocity (reaches the goal and, on the way, the left wall) or at random
+        if episode % 2 == 0:
+            return 2 if state[1] >= 0 else 0
+        return int(rng.integers(0, 3))
     if kind == MOUNTAIN_CAR_CONTINUOUS:
         if episode % 2 == 0:
             return float(np.float32(math.copysign(rng.uniform(0.5, 1.2), state[1] if state[1] != 0 else 1.0)))
@@ -154,7 +219,7 @@ def teacher_forced_trace(kind, steps, seed):
     sd, od = STATE_DIM[kind], OBS_DIM[kind]
     out = {
         "state": np.zeros((steps, sd), np.float32), "count": np.zeros(steps, np.uint32),
-        "action": np.zeros(steps, np.float32 if kind != ACROBOT else np.uint8),
+        "action": np.zeros(steps, np.float32 if kind in (MOUNTAIN_CAR_CONTINUOUS, PENDULUM) else np.uint8),
         "next_state": np.zeros((steps, sd), np.float64), "obs": np.zeros((steps, od), np.float64),
         "reward": np.zeros(steps, np.float64), "terminated": np.zeros(steps, np.uint8),
         "truncated": np.zeros(steps, np.uint8), "seam": np.zeros(steps, np.uint8),
@@ -163,13 +228,19 @@ def teacher_forced_trace(kind, steps, seed):
     count, episode = 0, 0
     for t in range(steps):
         a = policy(kind, rng, state.astype(np.float64), episode)
-        nxt, obs, reward, terminated, seam = STEP[kind](state.astype(np.float64), a)
         count_after = count + 1
-        truncated = count_after >= TIME_LIMIT[kind]  # gymnasium.wrappers.TimeLimit
+        if kind == CARTPOLE:
+            nxt, obs, reward, terminated, truncated, seam = cartpole_step(state.astype(np.float64), a, count)
+        else:
+            nxt, obs, reward, terminated, seam = STEP[kind](state.astype(np.float64), a)
+            truncated = TIME_LIMIT[kind] > 0 and count_after >= TIME_LIMIT[kind]  # gymnasium.wrappers.TimeLimit
+        # MountainCar-v0 has no limit: a random-policy episode is simply abandoned after 300 steps (a teacher-forced
+        # trace may restart anywhere; the recorded answer of that step is untouched)
+        abandon = kind == MOUNTAIN_CAR and count_after >= 300 and not terminated
         out["state"][t], out["count"][t], out["action"][t] = state, count, a
         out["next_state"][t], out["obs"][t], out["reward"][t] = nxt, obs, reward
         out["terminated"][t], out["truncated"][t], out["seam"][t] = terminated, truncated, seam
-        if terminated or truncated:
+        if terminated or truncated or abandon:
             state, count, episode = RESET[kind](rng).astype(np.float32), 0, episode + 1
         else:
             state, count = nxt.astype(np.float32), count_after

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""10^4-step teacher-forced known-answer traces for the three kinds the reference does not implement
-(MountainCarContinuous-v0, Pendulum-v1, Acrobot-v1), computed by the independent float64 transcription of the
-Gymnasium equations in tests/f64_gymnasium.py -- NOT by the oracle or the device code.  Gymnasium itself is not
+"""10^4-step teacher-forced known-answer traces of all five kinds, computed by the independent float64 transcription
+in tests/f64_gymnasium.py -- NOT by the oracle or the device code: the three kinds the reference does not implement
+(MountainCarContinuous-v0, Pendulum-v1, Acrobot-v1; Gymnasium's equations) and CartPole-v1 / MountainCar-v0 (the
+reference's equations), whose traces reach the 500-step truncation, the wall and the goal that the reference's
+100-step fixtures never do.  Gymnasium itself is not
 installed in this image, so these are the closest thing to an external answer this image allows:
 SURVEY rows A6-A8 stay "parity unpinned", but north_star's 1e-5 bar is exercised over 10^4-step traces.
 
@@ -21,7 +23,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 import f64_gymnasium as g  # noqa: E402
 
 STEPS = 10_000
-CASES = {"mountain_car_continuous": (g.MOUNTAIN_CAR_CONTINUOUS, 0xA6), "pendulum": (g.PENDULUM, 0xA7),
+CASES = {"cartpole": (g.CARTPOLE, 0xA2), "mountain_car": (g.MOUNTAIN_CAR, 0xA5),
+         "mountain_car_continuous": (g.MOUNTAIN_CAR_CONTINUOUS, 0xA6), "pendulum": (g.PENDULUM, 0xA7),
          "acrobot": (g.ACROBOT, 0xA8)}
 
 if __name__ == "__main__":

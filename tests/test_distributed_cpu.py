@@ -29,13 +29,20 @@ def worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from modurl_gym_b200.distributed import all_reduce_stats_vector, max_over_ranks, shard_range
+    from modurl_gym_b200.distributed import all_reduce_stats_vector, exchange_unique_id, max_over_ranks, shard_range
 
     begin, end = shard_range(TOTAL, rank, world)
     (obs, rew, flg, dones), vec = play(begin, end)
     total = all_reduce_stats_vector(torch.from_numpy(vec.copy()))
     slowest = max_over_ranks(10.0 + rank, "cpu")
-    q.put((rank, begin, end, obs[-1], int(dones), tuple(total), slowest))
+    # the rendezvous of the native NCCL communicator (NativeNcclComm): rank 0 draws the 128-byte id, every rank
+    # receives it through the process group; only rank 0's generator may run
+    def make_id():
+        assert rank == 0
+        return bytes((7 * i + 3) & 0xFF for i in range(128))
+
+    uid = exchange_unique_id(make_id, rank, "cpu")
+    q.put((rank, begin, end, obs[-1], int(dones), tuple(total), slowest, uid))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,6 +69,7 @@ def test_two_rank_sharding_and_stats_allreduce():
         assert g[5][:4] == tuple(int(x) for x in whole_vec[:4])
         assert g[5][4] == pytest.approx(whole_vec[4])
         assert g[6] == 11.0
+        assert g[7] == bytes((7 * i + 3) & 0xFF for i in range(128))  # both ranks hold rank 0's unique id
 
 
 def test_shard_range_properties():
