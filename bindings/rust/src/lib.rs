@@ -4,6 +4,7 @@
 //! The scalar trait is `fn reset(&mut self) -> Result<Tensor>` / `fn step(&mut self, action: Tensor) ->
 //! Result<StepInfo>`; here the tensors gain an env axis and are raw device pointers the embedding crate owns
 //! (candle's CUDA storage exposes them), so this crate has no tensor-library dependency.
+pub mod scalar;
 pub mod sys;
 
 use std::ffi::CStr;
@@ -97,6 +98,28 @@ impl GpuVecEnv {
     }
     pub fn num_envs(&self) -> u64 { self.num_envs }
     pub fn obs_dim(&self) -> usize { unsafe { sys::mgym_obs_dim(self.kind as i32) as usize } }
+    pub fn is_continuous(&self) -> bool { unsafe { sys::mgym_action_is_continuous(self.kind as i32) == 1 } }
+    /// Discrete(n): n; Box action spaces: 0.
+    pub fn num_actions(&self) -> i32 { unsafe { sys::mgym_num_actions(self.kind as i32) } }
+    /// observation_space() bounds (cartpole.rs:58-64, mountain_car.rs:42-43): (low, high), obs_dim values each.
+    pub fn observation_bounds(&self) -> (Vec<f32>, Vec<f32>) {
+        let (mut low, mut high) = (vec![0f32; self.obs_dim()], vec![0f32; self.obs_dim()]);
+        unsafe { sys::mgym_space_observation(self.kind as i32, low.as_mut_ptr(), high.as_mut_ptr()) };
+        (low, high)
+    }
+    /// action_space() bounds: Box kinds (low, high); Discrete(n) kinds (0, n - 1).
+    pub fn action_bounds(&self) -> (f32, f32) {
+        let (mut low, mut high) = (0f32, 0f32);
+        unsafe { sys::mgym_space_action(self.kind as i32, &mut low, &mut high) };
+        (low, high)
+    }
+    /// The current observation of every env as a host vector, component-major [obs_dim][N] (mgym_get_obs accepts
+    /// host pointers).
+    pub fn get_obs_host(&mut self) -> Result<Vec<f32>, MgymError> {
+        let mut obs = vec![0f32; self.obs_dim() * self.num_envs as usize];
+        check(unsafe { sys::mgym_get_obs(self.h, obs.as_mut_ptr(), self.stream) })?;
+        Ok(obs)
+    }
     pub fn set_stream(&mut self, stream: *mut c_void) { self.stream = stream; }
 
     /// Gym::reset for every env; `obs_out` is a device buffer of obs_dim * N floats.

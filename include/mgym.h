@@ -162,10 +162,12 @@ int mgym_set_reset_pool(mgym_env *env, const float *pool, uint64_t pool_len, voi
 
 /* ---- state injection / checkpoint (Testable::set_state) --------------------------- */
 /* state: SoA [state_dim][N]; steps, sbt: uint32[N] or NULL (-> 0 / None); device or host pointers.
- * sbt encodes steps_beyond_terminated: 0 = None, k+1 = Some(k). */
+ * sbt encodes steps_beyond_terminated: 0 = None, k+1 = Some(k).  steps = episode step counts
+ * (cartpole.rs:24 steps_since_reset); an auto-reset handle of a kind with a time limit <= 65535 keeps them in 16
+ * bits, so injected counts above 65535 are stored as 65535 (either way "past the limit": the next step truncates). */
 int mgym_set_state(mgym_env *env, const float *state, const uint32_t *steps, const uint32_t *sbt, void *stream);
 int mgym_get_state(mgym_env *env, float *state, uint32_t *steps, uint32_t *sbt, void *stream);
-int mgym_get_obs(mgym_env *env, float *obs_out, void *stream);
+int mgym_get_obs(mgym_env *env, float *obs_out, void *stream); /* current observation, [obs_dim][N]; device or host */
 /* Zero-copy view of the resident state rows ([state_dim][N]); for kinds whose observation is the
  * state (CartPole, MountainCar, MountainCarContinuous) this IS the observation buffer. */
 float *mgym_state_ptr(mgym_env *env);

@@ -180,6 +180,11 @@ class GpuVecEnv {
     check(mgym_stats_get(h_, &s, stream_));
     return s;
   }
+  // Sum of the statistics over the ranks of `nccl_comm` (an ncclComm_t), left as 5 doubles {episodes, terminated,
+  // truncated, length_sum, return_sum} in the caller's DEVICE buffer; the only collective of the path.
+  void stats_allreduce(void* nccl_comm, double* device_vec5) {
+    check(mgym_stats_allreduce(h_, nccl_comm, device_vec5, stream_));
+  }
 
   // ---- host-side conveniences ------------------------------------------------------------------------
   std::vector<float> reset_host() {

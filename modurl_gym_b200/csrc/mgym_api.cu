@@ -835,14 +835,25 @@ int mgym_get_obs(mgym_env* e, float* obs_out, void* stream) {
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((e->n + 255) / 256);
+  // like the state accessors, this one also takes a HOST array (scalar adapters, tests)
+  const bool host = is_host_pointer(obs_out);
+  const size_t bytes = sizeof(float) * kObsDim[e->kind] * (size_t)e->n;
+  float* dst = obs_out;
+  if (host) MGYM_CUDA(cudaMalloc(&dst, bytes));
   switch (e->kind) {
-    case 0: obs_kernel<0><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
-    case 1: obs_kernel<1><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
-    case 2: obs_kernel<2><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
-    case 3: obs_kernel<3><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
-    default: obs_kernel<4><<<blocks, 256, 0, st>>>(e->state, obs_out, e->n); break;
+    case 0: obs_kernel<0><<<blocks, 256, 0, st>>>(e->state, dst, e->n); break;
+    case 1: obs_kernel<1><<<blocks, 256, 0, st>>>(e->state, dst, e->n); break;
+    case 2: obs_kernel<2><<<blocks, 256, 0, st>>>(e->state, dst, e->n); break;
+    case 3: obs_kernel<3><<<blocks, 256, 0, st>>>(e->state, dst, e->n); break;
+    default: obs_kernel<4><<<blocks, 256, 0, st>>>(e->state, dst, e->n); break;
   }
-  MGYM_CUDA(cudaGetLastError());
+  cudaError_t err = cudaGetLastError();
+  if (host) {
+    if (err == cudaSuccess) err = cudaMemcpyAsync(obs_out, dst, bytes, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(dst);
+  }
+  if (err != cudaSuccess) return fail(MGYM_ERR_CUDA, "mgym_get_obs: %s", cudaGetErrorString(err));
   return MGYM_OK;
 }
 

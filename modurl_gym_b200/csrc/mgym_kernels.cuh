@@ -1437,7 +1437,13 @@ __global__ void counters_from_steps_kernel(const uint32_t* steps_or_null, typena
                                            uint64_t t, const unsigned long long* t_dev) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t_dev) t = *t_dev;
-  if (i < n) out[i] = cnt_encode<CNT>(steps_or_null ? steps_or_null[i] : 0u, t);
+  if (i < n) {
+    uint32_t steps = steps_or_null ? steps_or_null[i] : 0u;
+    // a 16-bit representation exists only below a time limit <= 65535: an injected count beyond it means "past the
+    // limit" whatever its value, and must not wrap around to "young episode"
+    if constexpr (sizeof(typename CounterType<CNT>::type) == 2) steps = min(steps, 0xFFFFu);
+    out[i] = cnt_encode<CNT>(steps, t);
+  }
 }
 template <int CNT>
 __global__ void steps_from_counters_kernel(const typename CounterType<CNT>::type* in, uint32_t* steps, uint64_t n,

@@ -261,6 +261,14 @@ class GpuVecEnv:
         _lib.check(self._lib.mgym_get_obs(self._h, _ptr(obs), self._stream()))
         return obs
 
+    def get_obs_host(self):
+        """The current observation as a host array [obs_dim, N] (mgym_get_obs also takes host pointers)."""
+        import numpy as np
+
+        out = np.empty((self.obs_dim, self.num_envs), dtype=np.float32)
+        _lib.check(self._lib.mgym_get_obs(self._h, _hptr(out), self._stream()))
+        return out
+
     def checkpoint(self):
         """The whole handle (state, counters, running returns, statistics, step/reset indices) as bytes."""
         size = self._lib.mgym_checkpoint_size(self._h)

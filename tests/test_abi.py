@@ -112,3 +112,17 @@ def test_rust_sys_declares_every_entry_point():
     text = open(os.path.join(ROOT, "bindings", "rust", "src", "sys.rs")).read()
     declared = set(re.findall(r"pub fn (mgym_[a-z_0-9]+)\(", text))
     assert declared == set(declared_symbols())
+
+
+def test_rust_sources_are_self_consistent():
+    """The Rust crate cannot be compiled here (no cargo/rustc), so at least: every sys:: function its wrappers call is
+    declared in sys.rs, and every GpuVecEnv method the scalar Gym adapter calls exists in lib.rs."""
+    src = os.path.join(ROOT, "bindings", "rust", "src")
+    sys_rs, lib_rs, scalar_rs = (open(os.path.join(src, f)).read() for f in ("sys.rs", "lib.rs", "scalar.rs"))
+    declared = set(re.findall(r"pub fn (mgym_[a-z_0-9]+)\(", sys_rs))
+    used = set(re.findall(r"sys::(mgym_[a-z_0-9]+)\(", lib_rs + scalar_rs))
+    assert used and used <= declared, used - declared
+    methods = set(re.findall(r"pub fn ([a-z_0-9]+)", lib_rs))
+    called = set(re.findall(r"self\.env\.([a-z_0-9]+)\(", scalar_rs)) | set(re.findall(r"GpuVecEnv::([a-z_0-9]+)\(", scalar_rs))
+    assert called and called <= methods, called - methods
+    assert "pub mod scalar;" in lib_rs and "track_returns" in sys_rs

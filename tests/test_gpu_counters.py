@@ -166,3 +166,25 @@ def test_checkpoint_rejects_a_different_configuration(gym):
     for cfg in (dict(), dict(sutton_barto_reward=True, is_euler=False)):
         with pytest.raises(gym.MgymError):
             gym.GpuVecEnv(0, n, seed=5, **cfg).restore(blob)
+
+
+def test_injected_counts_past_a_sixteen_bit_limit_still_truncate(gym, oracle):
+    """mgym_set_state with counts beyond what a 16-bit stamp can hold (CartPole: limit 500): whatever the value, the
+    env is past its limit and the next step truncates, exactly as the oracle's plain counter says."""
+    n = 1024
+    env = gym.GpuVecEnv(0, n, seed=3)
+    ref = oracle.VecState(0, n, auto_reset=1, seed=3)
+    env.reset(), ref.reset()
+    counts = np.array([0, 498, 499, 500, 65535, 65536, 65536 + 7, 70000, 1 << 31, 0xFFFFFFFE] * 103, np.uint32)[:n]
+    z = np.zeros((4, n), np.float32)
+    env.set_state(dev(z), dev(counts.view(np.int32)))
+    ref.state[:], ref.steps[:] = z, counts
+    a = np.zeros(n, np.uint8)
+    info = env.step(dev(a))
+    o, r, f = ref.step(a)
+    assert_bit_equal(host(info.flags), f, "flags")
+    assert_bit_equal(host(info.state), o, "obs after the same-step reset")
+    assert (f[counts >= 499] == 2).all() and (f[counts < 499] == 0).all()
+    s = env.stats()
+    assert (s.episodes, s.truncated) == (ref.stats.episodes, ref.stats.truncated)
+    env.close()

@@ -504,6 +504,33 @@ def test_sharded_handles_equal_one_handle(gym):
     assert tuple(tot[:4]) == tuple(whole.stats()[:4])
 
 
+@pytest.mark.parametrize("kind", range(5))
+def test_scalar_adapter_protocol(gym, oracle, kind):
+    """What bindings/rust/src/scalar.rs does, through the same entry points: ONE env in manual mode, host buffers only
+    (mgym_reset + mgym_get_obs with a host pointer, mgym_step_host), the caller resetting after done or truncated
+    exactly like the reference's own loops (cartpole.rs:460-471) -- compared with the oracle's scalar env."""
+    env = gym.GpuVecEnv(kind, 1, auto_reset=False, seed=17, validate_actions=True)
+    ref = oracle.VecState(kind, 1, auto_reset=0, seed=17)
+    rng = np.random.default_rng(kind)
+    obs, rew, flg = np.empty((env.obs_dim, 1), np.float32), np.empty(1, np.float32), np.empty(1, np.uint8)
+    env.reset()
+    assert_bit_equal(env.get_obs_host(), ref.reset(), "reset obs")
+    episodes = 0
+    for t in range(1100):  # beyond MountainCarContinuous' 999-step limit
+        a = random_actions(rng, kind, 1)
+        env.step_host(a, obs, rew, flg)
+        o, r, f = ref.step(a)
+        assert_bit_equal(obs, o, f"obs t={t}")
+        assert_bit_equal(rew, r, f"reward t={t}")
+        assert_bit_equal(flg, f, f"flags t={t}")
+        if f[0]:
+            episodes += 1
+            env.reset()
+            assert_bit_equal(env.get_obs_host(), ref.reset(), f"reset obs after t={t}")
+    assert episodes > 0 or kind == 1  # MountainCar-v0 never truncates (mountain_car.rs:328)
+    env.close()
+
+
 def test_step_host_round_trip(gym, oracle):
     n = 4096
     env = gym.GpuVecEnv(0, n, seed=2)
