@@ -37,9 +37,12 @@
  *                   an env whose step returns terminated or truncated is reset in the
  *                   same call; obs_out holds the post-reset observation, reward/flags the
  *                   finishing step's values, final_obs_out (optional) the pre-reset obs.
- *   Reset states come from a counter-based Philox4x32-10 stream keyed by
- *   (seed; global env index, step index), so results do not depend on launch
- *   geometry or on how envs are sharded over GPUs; or from an injected pool
+ *   Reset states come from a counter-based Philox4x32-10 stream keyed by the seed; the counter is
+ *   (global env index, reset call index) for mgym_reset and (global env index, step index at which
+ *   the episode that just finished BEGAN) for a same-step auto-reset, so results do not depend on
+ *   launch geometry, on the mix of mgym_step / mgym_rollout calls or on how envs are sharded over
+ *   GPUs -- and the state an env will restart from is known as soon as its episode starts, which
+ *   lets the rollout kernel draw it ahead of time.  Or they come from an injected pool
  *   (mgym_set_reset_pool) for parity runs.
  *
  * Errors: every function returns 0 on success or a negative mgym_status; the message is

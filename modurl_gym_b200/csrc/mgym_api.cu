@@ -330,7 +330,6 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
         return launch_step_tma<KIND, CNT_S16>(e, p, st);
       } else {
         switch (e->cnt_mode) {
-          case CNT_NONE: return launch_step_tma<KIND, CNT_NONE>(e, p, st);
           case CNT_S16: return launch_step_tma<KIND, CNT_S16>(e, p, st);
           case CNT_S32_LAZY: return launch_step_tma<KIND, CNT_S32_LAZY>(e, p, st);
           default: return launch_step_tma<KIND, CNT_S32>(e, p, st);
@@ -369,7 +368,6 @@ int dispatch_mode(const mgym_env* e, const KernelParams& p, cudaStream_t st) {
     MGYM_LAUNCH(true, CNT_S16);
   } else {
     switch (e->cnt_mode) {  // these kernels hold the count in registers: a lazy stamp is an ordinary one here
-      case CNT_NONE: MGYM_LAUNCH(true, CNT_NONE);
       case CNT_S16: MGYM_LAUNCH(true, CNT_S16);
       default: MGYM_LAUNCH(true, CNT_S32);
     }
@@ -403,7 +401,6 @@ int launch_reset_kind(const mgym_env* e, const KernelParams& p, const uint8_t* m
     else reset_kernel<KIND, CNT_><<<blocks, 256, 0, st>>>(p, mask, e->n_resets);                \
   } while (0)
   switch (e->cnt_mode) {
-    case CNT_NONE: MGYM_RESET(CNT_NONE); break;
     case CNT_U16: MGYM_RESET(CNT_U16); break;
     case CNT_U32: MGYM_RESET(CNT_U32); break;
     case CNT_S16: MGYM_RESET(CNT_S16); break;
@@ -635,10 +632,11 @@ int mgym_create(int kind, uint64_t num_envs, int device_ordinal, uint64_t seed, 
     e->cnt_mode = CNT_S16;
   } else if (cfg.max_episode_steps > 65535) {
     e->cnt_mode = CNT_S32;
-  } else if (cfg.track_stats) {
-    e->cnt_mode = CNT_S32_LAZY;  // no time limit: only the statistics want the episode length
   } else {
-    e->cnt_mode = CNT_NONE;  // MountainCar-v0 as in the reference: no counter at all
+    // no time limit: only a FINISHED env needs its episode length (it keys the reset stream and feeds the
+    // statistics), so the stamp is not touched by a step until then -- MountainCar-v0 moves no counter, like the
+    // reference (mountain_car.rs:10-23)
+    e->cnt_mode = CNT_S32_LAZY;
   }
 
   DeviceGuard guard(device_ordinal);

@@ -31,6 +31,9 @@
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
 
+#ifndef MGYM_RESET_REFILL_PERIOD
+#define MGYM_RESET_REFILL_PERIOD 3  // rollout, kinds with PREFETCH_RESETS: one slot's reset state is redrawn every N steps
+#endif
 #ifndef MGYM_ACT_RING
 #define MGYM_ACT_RING 8  // rollout: steps of action look-ahead staged in shared memory (power of two)
 #endif
@@ -55,14 +58,15 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // Per-env episode step count, as the handle keeps it between launches:
-//   CNT_NONE      nothing (no time limit, no statistics: MountainCar-v0 exactly as the reference, mountain_car.rs:10-23)
+//   CNT_NONE      nothing.  Not used by handles any more: an auto-reset handle always knows the length of a finished
+//                 episode (it keys the reset stream, see reset_pending), a manual one keeps the reference's counters
 //   CNT_U16/U32   the count itself, read AND written by every step (manual mode = the reference's steps_since_reset,
 //                 cartpole.rs:24; CNT_U16 is the round-1 CartPole form, kept for A/B measurements)
 //   CNT_S16/S32   a START STAMP: the handle's step index t at which the episode began (mod 2^16 / 2^32).  The count is
 //                 (t - stamp), so a step only READS the stamp; it is written when an episode ends (by the lane that
 //                 owns the finished env) -- 2 or 4 bytes read per env-step instead of a read and a write.
-//   CNT_S32_LAZY  the same stamp for kinds without a time limit, where only the statistics need the episode length:
-//                 not even read by a step unless the env finished (MountainCar-v0 with statistics: 22 B per env-step,
+//   CNT_S32_LAZY  the same stamp for kinds without a time limit, where only a FINISHED env needs its episode length
+//                 (statistics, reset stream): not even read by a step unless the env finished (MountainCar-v0: 22 B per env-step,
 //                 the SURVEY 8(d) contract figure, instead of 30).  Kernels that keep the count in registers anyway
 //                 (rollout, the LDG step form) treat it as CNT_S32.
 enum CounterMode : int { CNT_NONE = 0, CNT_U16 = 1, CNT_U32 = 2, CNT_S16 = 3, CNT_S32 = 4, CNT_S32_LAZY = 5 };
@@ -288,23 +292,46 @@ struct Group {
 //                   tallies from the packed flags word and hands the finished envs to its reset warp.
 enum ResetMode : int { RESET_IN_PLACE = 0, RESET_BY_CALLER = 2 };
 
-// Draws the reset states of the slots in `pending` (bit v = slot v), one slot per lane per pass.
+// The reset state of an env is a function of (seed; global env index, step index at which the episode that just
+// finished BEGAN): Philox counter (g, t_start).  The start index is known for the whole episode (t_start = t - count
+// at the entry of step t), so -- unlike a stream keyed by the finishing step -- the state an env will restart
+// from can be drawn at any time before it is needed: the rollout kernel draws it ahead of time with full warps.
+__device__ __forceinline__ uint64_t episode_start(uint64_t t, uint32_t count_after) { return t + 1ull - (uint64_t)count_after; }
+
+// Reset states drawn ahead of time (rollout kernel, kinds with Env::PREFETCH_RESETS): per thread one slot of shared
+// memory per env, and a validity bit per slot.  A null `smem` means "none".
+struct ResetPrefetch {
+  float4* smem = nullptr;  // this thread's slot 0; slot v at smem[v * 256]
+  uint32_t valid = 0;      // bit v: slot v holds the state for the END of env v's current episode
+};
+
+// Draws the reset states of the slots in `pending` (bit v = slot v), one slot per lane per pass.  g.steps[] are the
+// counts AFTER the finishing step (they are cleared here).
 template <int KIND, int V>
 __device__ __forceinline__ void reset_pending(const KernelParams& p, uint64_t base, uint64_t t, uint32_t pending,
-                                              Group<KIND, V>& g) {
+                                              Group<KIND, V>& g, ResetPrefetch* pre = nullptr) {
   using E = Env<KIND>;
   while (pending) {
     const int sel = __ffs(pending) - 1;
     pending &= pending - 1;
     const uint64_t gid = p.env_base + base + sel;
+    uint32_t count = g.steps[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) count = (v == sel) ? g.steps[v] : count;
     float ns[E::SD], no[E::OD];
     if (p.reset_pool) {
       const uint64_t j = (gid + t) % p.pool_len;
 #pragma unroll
       for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
-    } else {
-      E::reset(philox_env(p.keys, gid, t, TAG_AUTO_RESET), ns);
+    } else if (pre && ((pre->valid >> sel) & 1u)) {
+      const float4 q = pre->smem[sel * 256];
+      const float qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int c = 0; c < E::SD && c < 4; ++c) ns[c] = qs[c];
+    } else {  // also: finished again before its slot was redrawn.  (Out of line this draw cost the hot loop 3 %.)
+      E::reset(philox_env(p.keys, gid, episode_start(t, count), TAG_AUTO_RESET), ns);
     }
+    if (pre) pre->valid &= ~(1u << sel);  // the new episode's own reset state has not been drawn yet
     if constexpr (!E::OBS_IS_STATE) E::obs(ns, no);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -550,6 +577,7 @@ __global__ void __launch_bounds__(256, MGYM_MIN_BLOCKS) step_kernel(const __grid
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD;
   static_assert(!cnt_is_lazy(CNT) && (AUTO || !cnt_is_stamp(CNT)), "the host maps CNT_S32_LAZY to CNT_S32 here");
+  static_assert(!AUTO || CNT != CNT_NONE, "auto-reset needs the episode length: it keys the reset stream");
   StatAcc acc;
   const uint64_t groups = p.n / V;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -721,8 +749,10 @@ struct TmaLayout {
   static constexpr uint32_t STAGE_BYTES = (OFF_SBT + SBT_BYTES + 127u) & ~127u;
   static constexpr uint32_t BAR_BYTES = 128;  // full[STAGES], empty[STAGES], tile id of each stage
   static_assert(24 * TMA_STAGES <= 128, "barriers and tile ids must fit BAR_BYTES");
-  // reset queues: per buffer {q_full, q_empty mbarriers, tile id, count} (32 B) + TMA_TILE uint16 env indices
-  static constexpr uint32_t QUEUE_BYTES = TMA_RESET_BUFFERS * (32 + TMA_TILE * 2);
+  // reset queues: per buffer {q_full, q_empty mbarriers, tile id, count} (32 B) + per finished env its uint16 index in
+  // the tile and the uint32 length of the episode that ended (the reset stream is keyed by its start)
+  static constexpr uint32_t QUEUE_STRIDE = 32 + TMA_TILE * 2 + TMA_TILE * 4;
+  static constexpr uint32_t QUEUE_BYTES = TMA_RESET_BUFFERS * QUEUE_STRIDE;
   static constexpr uint32_t OFF_QUEUE = BAR_BYTES + TMA_STAGES * STAGE_BYTES;
   static constexpr uint32_t SMEM_BYTES = 128 + OFF_QUEUE + QUEUE_BYTES;
 };
@@ -752,6 +782,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   using cnt_t = typename CounterType<CNT>::type;
   constexpr int SD = E::SD, OD = E::OD, V = 4;
   static_assert(AUTO || !cnt_is_stamp(CNT), "manual mode keeps the reference's own counters");
+  static_assert(!AUTO || CNT != CNT_NONE, "auto-reset needs the episode length: it keys the reset stream");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tma::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
@@ -760,12 +791,14 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
   volatile uint64_t* tile_slot =
       reinterpret_cast<volatile uint64_t*>(smem_raw + (smem_base + 16 * TMA_STAGES - tma::smem_u32(smem_raw)));
   // reset queues, one per buffer: [q_full mbarrier][q_empty mbarrier][tile id u64][count u32, pad][uint16 x TMA_TILE]
-  constexpr uint32_t QSTRIDE = 32 + TMA_TILE * 2;
+  // [uint32 x TMA_TILE]
+  constexpr uint32_t QSTRIDE = L::QUEUE_STRIDE;
   const uint32_t queue0 = smem_base + L::OFF_QUEUE;
   uint8_t* const queue_ptr = smem_raw + (queue0 - tma::smem_u32(smem_raw));
   auto q_tile = [&](uint32_t b) { return reinterpret_cast<volatile uint64_t*>(queue_ptr + b * QSTRIDE + 16); };
   auto q_count = [&](uint32_t b) { return reinterpret_cast<uint32_t*>(queue_ptr + b * QSTRIDE + 24); };
   auto q_items = [&](uint32_t b) { return reinterpret_cast<uint16_t*>(queue_ptr + b * QSTRIDE + 32); };
+  auto q_lengths = [&](uint32_t b) { return reinterpret_cast<uint32_t*>(queue_ptr + b * QSTRIDE + 32 + TMA_TILE * 2); };
   const uint32_t data0 = smem_base + L::BAR_BYTES;
   const uint64_t n_tiles = p.n / TMA_TILE;
   const bool track_ret = AUTO && !E::ANALYTIC_RETURN && p.ep_return != nullptr;
@@ -836,6 +869,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       if (tile >= n_tiles) break;
       const uint32_t count = *q_count(qb);
       const uint16_t* items = q_items(qb);
+      const uint32_t* lengths = q_lengths(qb);
       const uint64_t tile_base = p.first + tile * TMA_TILE;
       for (uint32_t j = lane; j < count; j += 32) {
         const uint64_t local = tile_base + items[j];
@@ -846,7 +880,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
 #pragma unroll
           for (int c = 0; c < SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + k];
         } else {
-          E::reset(philox_env(p.keys, gid, t_now, TAG_AUTO_RESET), ns);
+          E::reset(philox_env(p.keys, gid, episode_start(t_now, lengths[j]), TAG_AUTO_RESET), ns);
         }
 #pragma unroll
         for (int c = 0; c < SD; ++c) p.state[(uint64_t)c * p.ld + local] = ns[c];
@@ -945,10 +979,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
         tally_packed<KIND, V, true>(fin, g, acc);
         uint32_t pos = atomicAdd(q_count(qb), (uint32_t)__popc((fin | (fin >> 1)) & 0x01010101u));
         uint16_t* items = q_items(qb);
+        uint32_t* lengths = q_lengths(qb);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           if ((fin >> (8 * v)) & 0xffu) {
-            items[pos++] = (uint16_t)(tid * V + v);
+            items[pos] = (uint16_t)(tid * V + v);
+            lengths[pos++] = g.steps[v];
             g.steps[v] = 0u;
             g.ret[v] = 0.0f;
           }
@@ -1045,10 +1081,19 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   constexpr int SD = E::SD, OD = E::OD;
   static_assert(!FULL || (AUTO && V == 4), "the FULL form is built for the vector auto-reset path only");
   static_assert(!cnt_is_lazy(CNT) && (AUTO || !cnt_is_stamp(CNT)), "the host maps CNT_S32_LAZY to CNT_S32 here");
+  static_assert(!AUTO || CNT != CNT_NONE, "auto-reset needs the episode length: it keys the reset stream");
   constexpr int ACT_RING = MGYM_ACT_RING;
   static_assert((ACT_RING & (ACT_RING - 1)) == 0, "power of two");
   constexpr uint32_t RING_STRIDE = 256 * V * sizeof(act_t);  // one row of the CTA: 256 threads x V actions
   __shared__ __align__(16) act_t act_ring[V == 4 ? ACT_RING : 1][256 * V];
+  // CartPole finishes an env every ~22 steps: ~6 of a warp's 128 envs per step, served by a divergent pass whose
+  // Philox block + four f64 -> f32 uniforms run at ~6 of 32 lanes -- a third of all issued instructions.  The reset
+  // stream is keyed by the START of the finished episode (reset_pending), so the state an env will restart from is
+  // drawn AHEAD of time with all 32 lanes busy: all four slots when a warp tile is loaded, then one slot every
+  // MGYM_RESET_REFILL_PERIOD steps, into per-thread shared memory.  The divergent pass then only picks it up; an env
+  // that finishes again before its slot was redrawn (bit clear in `valid`) draws in the pass as before.
+  constexpr bool PREFETCH = AUTO && V == 4 && E::PREFETCH_RESETS;
+  __shared__ float4 next_reset[PREFETCH ? 4 : 1][256];
   StatAcc acc;
   uint32_t dones = 0;  // finished env-steps of this lane's groups
   const uint64_t groups = p.n / V;
@@ -1146,6 +1191,27 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     // One step of this warp tile.  `trusted_tag` selects the form without per-step precondition tests; the
     // return value says whether the invariant behind it still holds (it can only break when a reset state
     // comes from an injected pool, and is re-checked right there, under the same rare branch).
+    ResetPrefetch pre;
+    [[maybe_unused]] uint32_t refill_slot = 3, refill_wait = 0;
+    [[maybe_unused]] auto draw_ahead = [&](uint32_t slot, uint64_t t) {  // t = index of the step about to run
+      uint32_t count = g.steps[0];
+#pragma unroll
+      for (int v = 1; v < V; ++v) count = ((uint32_t)v == slot) ? g.steps[v] : count;
+      float ns[4] = {0.0f, 0.0f, 0.0f, 0.0f}, full[SD];
+      E::reset(philox_env(p.keys, p.env_base + base + slot, t - (uint64_t)count, TAG_AUTO_RESET), full);
+#pragma unroll
+      for (int c = 0; c < SD && c < 4; ++c) ns[c] = full[c];
+      pre.smem[slot * 256] = make_float4(ns[0], ns[1], ns[2], ns[3]);
+      pre.valid |= 1u << slot;
+    };
+    if constexpr (PREFETCH) {
+      static_assert(SD <= 4, "one float4 per env");
+      pre.smem = &next_reset[0][threadIdx.x];
+      if (!p.reset_pool) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) draw_ahead(v, t_first);
+      }
+    }
     // the actions of step `row`: out of the ring (and the row ACT_RING steps later starts on its way into the slot
     // just read), or straight from global memory for scalar lanes
     auto fetch_row = [&](RawActions<act_t, V>& dst, uint32_t row) {
@@ -1221,7 +1287,7 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
           uint32_t pending = 0;
 #pragma unroll
           for (int v = 0; v < V; ++v) pending |= ((wf >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
-          reset_pending<KIND, V>(p, base, t, pending, g);
+          reset_pending<KIND, V>(p, base, t, pending, g, PREFETCH ? &pre : nullptr);
           if constexpr (TRUSTED && E::HAS_TRUSTED) {
             if (p.reset_pool) still = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));
           }
@@ -1268,6 +1334,13 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     };
 #pragma unroll 1
     for (uint32_t kk = 0; kk < p.K; ++kk) {
+      if constexpr (PREFETCH) {
+        if (++refill_wait == MGYM_RESET_REFILL_PERIOD && !p.reset_pool) {
+          refill_wait = 0;
+          refill_slot = (refill_slot + 1u) & 3u;
+          draw_ahead(refill_slot, t_first + kk);
+        }
+      }
       RawActions<act_t, V> a_cur;
       fetch_row(a_cur, kk);
       step_any(kk, a_cur);

@@ -703,7 +703,9 @@ static inline void vec_step_one(int kind, const oracle_config *cfg, uint64_t i, 
       uint64_t j = (g + t) % pool_len;
       for (int c = 0; c < sd; ++c) st[c] = reset_pool[(uint64_t)c * pool_len + j];
     } else {
-      oracle_reset_state(kind, cfg->seed, g, t, 0u, st);
+      /* keyed by the step index at which the finished episode BEGAN (t + 1 - its length): known for the whole
+         episode, so the device may draw the state ahead of time (rollout_kernel); see mgym.h "Reset states" */
+      oracle_reset_state(kind, cfg->seed, g, t + 1u - (uint64_t)my_steps, 0u, st);
     }
     my_steps = 0;
     my_sbt = ORACLE_SBT_NONE;
