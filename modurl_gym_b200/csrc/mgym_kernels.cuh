@@ -31,9 +31,6 @@
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
 
-#ifndef MGYM_RESET_REFILL_PERIOD
-#define MGYM_RESET_REFILL_PERIOD 3  // rollout, kinds with PREFETCH_RESETS: one slot's reset state is redrawn every N steps
-#endif
 #ifndef MGYM_ACT_RING
 #define MGYM_ACT_RING 8  // rollout: steps of action look-ahead staged in shared memory (power of two)
 #endif
@@ -323,12 +320,12 @@ __device__ __forceinline__ void reset_pending(const KernelParams& p, uint64_t ba
       const uint64_t j = (gid + t) % p.pool_len;
 #pragma unroll
       for (int c = 0; c < E::SD; ++c) ns[c] = p.reset_pool[(uint64_t)c * p.pool_len + j];
-    } else if (pre && ((pre->valid >> sel) & 1u)) {
+    } else if (pre) {  // the caller has redrawn every pending slot that was not valid
       const float4 q = pre->smem[sel * 256];
       const float qs[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int c = 0; c < E::SD && c < 4; ++c) ns[c] = qs[c];
-    } else {  // also: finished again before its slot was redrawn.  (Out of line this draw cost the hot loop 3 %.)
+    } else {
       E::reset(philox_env(p.keys, gid, episode_start(t, count), TAG_AUTO_RESET), ns);
     }
     if (pre) pre->valid &= ~(1u << sel);  // the new episode's own reset state has not been drawn yet
@@ -1089,9 +1086,9 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
   // CartPole finishes an env every ~22 steps: ~6 of a warp's 128 envs per step, served by a divergent pass whose
   // Philox block + four f64 -> f32 uniforms run at ~6 of 32 lanes -- a third of all issued instructions.  The reset
   // stream is keyed by the START of the finished episode (reset_pending), so the state an env will restart from is
-  // drawn AHEAD of time with all 32 lanes busy: all four slots when a warp tile is loaded, then one slot every
-  // MGYM_RESET_REFILL_PERIOD steps, into per-thread shared memory.  The divergent pass then only picks it up; an env
-  // that finishes again before its slot was redrawn (bit clear in `valid`) draws in the pass as before.
+  // drawn AHEAD of time with all 32 lanes busy, into per-thread shared memory, and the divergent pass only picks it
+  // up.  A slot is (re)drawn for the whole warp when some lane is about to consume it without a valid state (one
+  // REDUX per step decides): every ~10 steps per slot in steady state, since an env must finish twice in between.
   constexpr bool PREFETCH = AUTO && V == 4 && E::PREFETCH_RESETS;
   __shared__ float4 next_reset[PREFETCH ? 4 : 1][256];
   StatAcc acc;
@@ -1192,13 +1189,14 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     // return value says whether the invariant behind it still holds (it can only break when a reset state
     // comes from an injected pool, and is re-checked right there, under the same rare branch).
     ResetPrefetch pre;
-    [[maybe_unused]] uint32_t refill_slot = 3, refill_wait = 0;
-    [[maybe_unused]] auto draw_ahead = [&](uint32_t slot, uint64_t t) {  // t = index of the step about to run
+    // Redraws slot `slot` of EVERY lane (full warp): the state the lane's env in that slot restarts from when its
+    // current episode ends.  t_next = index of the next step to run; g.steps = counts at its entry.
+    [[maybe_unused]] auto draw_ahead = [&](uint32_t slot, uint64_t t_next) {
       uint32_t count = g.steps[0];
 #pragma unroll
       for (int v = 1; v < V; ++v) count = ((uint32_t)v == slot) ? g.steps[v] : count;
       float ns[4] = {0.0f, 0.0f, 0.0f, 0.0f}, full[SD];
-      E::reset(philox_env(p.keys, p.env_base + base + slot, t - (uint64_t)count, TAG_AUTO_RESET), full);
+      E::reset(philox_env(p.keys, p.env_base + base + slot, t_next - (uint64_t)count, TAG_AUTO_RESET), full);
 #pragma unroll
       for (int c = 0; c < SD && c < 4; ++c) ns[c] = full[c];
       pre.smem[slot * 256] = make_float4(ns[0], ns[1], ns[2], ns[3]);
@@ -1207,10 +1205,6 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     if constexpr (PREFETCH) {
       static_assert(SD <= 4, "one float4 per env");
       pre.smem = &next_reset[0][threadIdx.x];
-      if (!p.reset_pool) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) draw_ahead(v, t_first);
-      }
     }
     // the actions of step `row`: out of the ring (and the row ACT_RING steps later starts on its way into the slot
     // just read), or straight from global memory for scalar lanes
@@ -1287,6 +1281,19 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
           uint32_t pending = 0;
 #pragma unroll
           for (int v = 0; v < V; ++v) pending |= ((wf >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
+          if constexpr (PREFETCH) {
+            // Slots about to be consumed whose state is not there (never drawn in this tile, or consumed since):
+            // redraw those slots for the WHOLE warp, so that the divergent pass below only ever picks states up.
+            // In steady state a slot is redrawn every ~10 steps (an env must finish twice in between).
+            if (!p.reset_pool) {
+              uint32_t need = __reduce_or_sync(0xffffffffu, pending & ~pre.valid);
+              while (need) {
+                const uint32_t slot = __ffs(need) - 1;
+                need &= need - 1;
+                draw_ahead(slot, t + 1);
+              }
+            }
+          }
           reset_pending<KIND, V>(p, base, t, pending, g, PREFETCH ? &pre : nullptr);
           if constexpr (TRUSTED && E::HAS_TRUSTED) {
             if (p.reset_pool) still = __all_sync(0xffffffffu, group_trusted<KIND, V>(g));
@@ -1334,13 +1341,6 @@ __global__ void __launch_bounds__(256, rollout_min_blocks<KIND>()) rollout_kerne
     };
 #pragma unroll 1
     for (uint32_t kk = 0; kk < p.K; ++kk) {
-      if constexpr (PREFETCH) {
-        if (++refill_wait == MGYM_RESET_REFILL_PERIOD && !p.reset_pool) {
-          refill_wait = 0;
-          refill_slot = (refill_slot + 1u) & 3u;
-          draw_ahead(refill_slot, t_first + kk);
-        }
-      }
       RawActions<act_t, V> a_cur;
       fetch_row(a_cur, kk);
       step_any(kk, a_cur);
