@@ -98,7 +98,8 @@ void oracle_env_obs(int kind, const float *state, float *obs);
 /*
  * Batched driver with exactly the semantics of mgym_step (include/mgym.h):
  * SoA state[state_dim][ld], per-env counters, optional outputs may be NULL.
- * t = index of this step since creation (selects the auto-reset Philox counter).
+ * t = index of this step since creation.  An env that finishes is reset from the Philox block with counter
+ * (global env index, t + 1 - episode length) = (g, step index at which the finished episode began).
  * reset_pool (optional, SoA [state_dim][pool_len]): injected reset states,
  * entry (g + t) % pool_len, replaces Philox.
  */
