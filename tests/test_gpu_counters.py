@@ -189,3 +189,43 @@ def test_injected_counts_past_a_sixteen_bit_limit_still_truncate(gym, oracle):
     s = env.stats()
     assert (s.episodes, s.truncated) == (ref.stats.episodes, ref.stats.truncated)
     env.close()
+
+
+@pytest.mark.parametrize("n", [1024, 515])
+def test_cartpole_rollout_reset_sources(gym, oracle, n):
+    """The CartPole rollout draws reset states AHEAD of time, keyed by the start of the running episode
+    (rollout_kernel, Env<0>::PREFETCH_RESETS).  Three situations the ordinary parity runs reach only by chance:
+    every env of every lane finishing in the very first step of a launch (no state drawn yet, four pending slots
+    per lane), an injected reset pool taking precedence over the drawn states, and going back to Philox after the
+    pool is removed -- trajectories, counts and statistics must be the oracle's throughout."""
+    seed, K = 21, 40
+    env = gym.GpuVecEnv(0, n, seed=seed)
+    ref = oracle.VecState(0, n, auto_reset=1, seed=seed)
+    rng = np.random.default_rng(n)
+    assert_bit_equal(host(env.reset()), ref.reset(), "reset")
+
+    def play(what, with_actions):
+        a = random_actions(rng, 0, (K, n)) if with_actions else None
+        out = env.rollout(K, None if a is None else dev(a))
+        o, r, f, dc = ref.rollout(K, a)
+        assert_bit_equal(host(out.flags), f, what + ": flags")
+        assert_bit_equal(host(out.obs), o, what + ": obs")
+        assert int(out.done_count.item()) == dc
+        check_counts(env, ref, what)
+
+    fallen = np.zeros((4, n), np.float32)
+    fallen[2] = 0.3  # beyond the 12-degree threshold: every env terminates in the first step
+    counts = rng.integers(0, 400, n).astype(np.uint32)
+    env.set_state(dev(fallen), dev(counts.view(np.int32)))
+    ref.state[:], ref.steps[:] = fallen, counts
+    play("all envs finish in step 0", True)
+    play("steady state, device policy", False)
+    pool = random_states(rng, 0, 61)
+    pool[2, ::3] = 0.25  # a third of the pool states terminate at once: envs that finish every step
+    env.set_reset_pool(dev(pool))
+    ref.set_reset_pool(pool)
+    play("injected pool", True)
+    env.set_reset_pool(None)
+    ref.set_reset_pool(None)
+    play("back to Philox", True)
+    env.close()
