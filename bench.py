@@ -309,7 +309,7 @@ class Ctx:
         clocks = self.sampler.window(w0, w1) if (self.rank == 0 and self.sampler) else None
         return sec, clocks
 
-    def calibrated(self, fn, seconds, windows=3, idle=0.25, min_reps=2, max_reps=100000):
+    def calibrated(self, fn, seconds, windows=3, idle=0.25, min_reps=2, max_reps=100000, counter=None):
         """warm-up (>= 3 calls), then `windows` timed regions of about `seconds` each with `idle` seconds of rest
         before each (the chip's power governor clocks a hot kernel down within milliseconds, and how far depends on
         what ran just before: every window starts from the same rested state).  Returns the BEST window (time, reps,
@@ -326,10 +326,13 @@ class Ctx:
         one = self.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 1e-6))
         reps = int(min(max_reps, max(min_reps, round(seconds / one))))
         best, all_sec = None, []
+        self.timed_launches = 0  # kernel launches inside the timed windows (`counter[0]` counts the caller's launches)
         for _ in range(windows):
             time.sleep(idle)
             fn()  # one untimed call: the first launch after an idle gap pays the clock ramp
+            before = counter[0] if counter else 0
             sec, clocks = self.timed(fn, reps)
+            self.timed_launches += (counter[0] - before) if counter else 0
             all_sec.append(sec)
             if best is None or sec < best[0]:
                 best = (sec, clocks)
@@ -398,7 +401,7 @@ def run_subconfig(ctx, m, spec, args, peak):
         contract = ROLLOUT_CONTRACT[kind]
         what = (f"fused rollout, {steps_per_pass} steps per pass as {K}-step launches over one reused "
                 f"[{K}][..][N] trajectory ring, actions read from a [{K}][N] ring")
-    sec, reps, clocks, windows = ctx.calibrated(one_pass, args.config_seconds)
+    sec, reps, clocks, windows = ctx.calibrated(one_pass, args.config_seconds, counter=launches)
     env_steps = float(n) * ctx.world * steps_per_pass * reps
     rate = env_steps / sec
     per_gpu_gbs = contract * (rate / ctx.world) / 1e9
@@ -415,7 +418,7 @@ def run_subconfig(ctx, m, spec, args, peak):
     env.close()
     del env
     torch.cuda.empty_cache()
-    return out, launches[0]
+    return out, ctx.timed_launches
 
 
 def run_mixed_suite(ctx, m, args, native_comm):
@@ -425,7 +428,7 @@ def run_mixed_suite(ctx, m, args, native_comm):
     NCCL entry point mgym_stats_allreduce on a raw ncclComm_t; both must agree."""
     torch, dist = ctx.torch, ctx.dist
     dev = ctx.device
-    K, launches = 16, 0
+    K = 16
     envs, bufs = [], []
     for kind, n in enumerate(MIXED_PER_GPU):
         n = max(1024, int(n * args.scale) // 1024 * 1024)
@@ -441,8 +444,8 @@ def run_mixed_suite(ctx, m, args, native_comm):
             env.rollout(K, None, obs=o, reward=r, flags=f, count_done=False)
             count[0] += 1
 
-    sec, reps, clocks, windows = ctx.calibrated(sweep, args.config_seconds)
-    launches = count[0]
+    sec, reps, clocks, windows = ctx.calibrated(sweep, args.config_seconds, counter=count)
+    launches = ctx.timed_launches
     steps = K * reps
     # the collective (off the per-step path): one all-reduce of the 5 x 5 statistics matrix
     mat = torch.stack([env.stats_tensor() for env in envs])

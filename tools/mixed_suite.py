@@ -42,7 +42,7 @@ def main():
     envs, bufs = [], []
     for kind, n in enumerate(PER_GPU):
         n = max(1024, int(n * args.scale) // 1024 * 1024)
-        env = m.GpuVecEnv(kind, n, device=local, seed=0x5EED, env_index_base=rank * n)
+        env = m.GpuVecEnv(kind, n, device=local, seed=0x5EED, env_index_base=rank * n, track_returns=True)
         env.reset()
         envs.append(env)
         K = args.chunk
