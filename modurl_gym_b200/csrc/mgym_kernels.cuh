@@ -31,6 +31,9 @@
 #define MGYM_TMA_MIN_BLOCKS 2
 #endif
 
+#ifndef MGYM_STEP_BATCH_PAIRS
+#define MGYM_STEP_BATCH_PAIRS false  // true: step_kernel_tma runs Acrobot as two batches of two envs (see step_group)
+#endif
 #ifndef MGYM_ACT_RING
 #define MGYM_ACT_RING 8  // rollout: steps of action look-ahead staged in shared memory (power of two)
 #endif
@@ -430,8 +433,9 @@ __device__ __forceinline__ uint32_t step_group(const KernelParams& p, bool count
     }
     if constexpr (BATCH_PAIRS && V == 4) {
       // two batches of two: half the loop body (Acrobot's rolled RK4 loop then stalls less on instruction
-      // fetch) for half the instruction-level parallelism.  Measured: +7 % in the per-call step kernel,
-      // -2 % in the rollout kernel, so only the former asks for it.
+      // fetch) for half the instruction-level parallelism.  With the scalar derivative this was +7 % in the
+      // per-call step kernel (-2 % in the rollout); with the packed f32x2 derivative a batch of two is ONE chain
+      // of packed operations, and the batch of four wins again (+4 %), so nobody asks for it now.
       using act_t = typename E::act_t;
       bool ok2[2];
       const act_t a01[2] = {action[0], action[1]}, a23[2] = {action[2], action[3]};
@@ -955,10 +959,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MGYM_TMA_MIN_BLOCKS) step_kernel_
       }
 #else
       if (want_final)
-        step_group<KIND, V, AUTO, true, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret, g,
+        step_group<KIND, V, AUTO, true, true, RESET_BY_CALLER, false, false, MGYM_STEP_BATCH_PAIRS>(p, true, base, t_now, action, track_ret, g,
                                                                                    acc);
       else
-        step_group<KIND, V, AUTO, false, true, RESET_BY_CALLER, false, false, true>(p, true, base, t_now, action, track_ret,
+        step_group<KIND, V, AUTO, false, true, RESET_BY_CALLER, false, false, MGYM_STEP_BATCH_PAIRS>(p, true, base, t_now, action, track_ret,
                                                                                     g, acc);
 #endif
       // Everything about this lane's finished envs sits in one branch: statistics from the packed flags word,
