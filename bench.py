@@ -629,14 +629,24 @@ def run_native(args, rank, local_rank, world):
     configs = {}
     if not args.no_configs:
         only = [s for s in args.only_configs.split(",") if s]
+        # a leg that fails (out of memory on a smaller GPU, say) is reported in its own entry; the headline line
+        # still prints.  Every rank runs the same code on the same sizes, so a failure is the same on all of them.
         for spec in SUBCONFIGS:
             if only and spec[0] not in only:
                 continue
-            configs[spec[0]], k = run_subconfig(ctx, m, spec, args, peak)
-            gpu_launches += k
+            try:
+                configs[spec[0]], k = run_subconfig(ctx, m, spec, args, peak)
+                gpu_launches += k
+            except Exception as e:
+                configs[spec[0]] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.empty_cache()
         if not only or "mixed_suite" in only:
-            configs["mixed_suite"], k = run_mixed_suite(ctx, m, args, native_comm)
-            gpu_launches += k
+            try:
+                configs["mixed_suite"], k = run_mixed_suite(ctx, m, args, native_comm)
+                gpu_launches += k
+            except Exception as e:
+                configs["mixed_suite"] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.empty_cache()
     if native_comm is not None:
         native_comm.close()
 

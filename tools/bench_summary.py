@@ -19,6 +19,9 @@ for f in sys.argv[1:]:
         print("  link", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in e["host_link"].items() if k != "how"})
     print(" native_nccl_allreduce:", d.get("native_nccl_allreduce"), " launches", d["gpu_launches"])
     for k, c in d.get("configs", {}).items():
+        if "error" in c:
+            print(f"  {k:38s} ERROR {c['error']}")
+            continue
         ck = c.get("clocks") or {}
         if k == "mixed_suite":
             print(f"  mixed_suite {c['suite_env_steps_per_s']:.3e}  {c['ms_per_sweep']:.3f} ms/sweep  allreduce {c['allreduce_ms']:.3f} ms  "
