@@ -518,13 +518,15 @@ def measure_host_link(ctx, nbytes=256 << 20, reps=4):
         return ctx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
     run(True, True)  # warm-up
-    t_d2h, t_h2d, t_both = run(True, False), run(False, True), run(True, True)
+    t_d2h = min(run(True, False) for _ in range(3))
+    t_h2d = min(run(False, True) for _ in range(3))
+    t_both = min(run(True, True) for _ in range(3))
     gb = nbytes * reps / 1e9
     out = {"d2h_GBps_per_gpu": gb / t_d2h, "h2d_GBps_per_gpu": gb / t_h2d,
            "duplex_d2h_GBps_per_gpu": gb / t_both, "duplex_total_GBps_per_gpu": 2 * gb / t_both,
            "aggregate_d2h_GBps": ctx.world * gb / t_d2h, "ranks_copying_at_once": ctx.world,
            "how": f"{reps} x {nbytes >> 20} MiB cudaMemcpyAsync per direction between pinned host memory and HBM, "
-                  f"all ranks at once, CUDA events, max over ranks"}
+                  f"all ranks at once, CUDA events, max over ranks, best of 3"}
     del d_a, d_b, h_in, h_out
     return out
 
@@ -617,7 +619,10 @@ def run_native(args, rank, local_rank, world):
 
     for _ in range(3):
         host_step()
-    e2e_s, e2e_clocks = ctx.timed(host_step, args.e2e_steps)
+    # best of three windows of e2e_steps each (the host side of a PCIe-bound call is noisy: other processes, page
+    # migration of the pinned buffers' first touch); the link ceiling below is taken the same way
+    e2e_windows = [ctx.timed(host_step, args.e2e_steps) for _ in range(3)]
+    e2e_s, e2e_clocks = min(e2e_windows, key=lambda w: w[0])
     h2d = h_act.numel() * h_act.element_size()
     d2h = sum(x.numel() * x.element_size() for x in (h_obs, h_rew, h_flg))
     link = measure_host_link(ctx)
@@ -670,6 +675,8 @@ def run_native(args, rank, local_rank, world):
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src},
             "e2e": {"value": float(n) * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                    "window_ms_per_step": [1e3 * w[0] / args.e2e_steps for w in e2e_windows],
+                    "timing": "best of the windows listed",
                     "path": "mgym_step_host: pinned host actions -> device, step, obs/reward/flags -> pinned host",
                     "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / e2e_s / 1e9,
                     "roofline": {"bound": "pcie", "achieved": d2h_rate, "peak": link["d2h_GBps_per_gpu"],
