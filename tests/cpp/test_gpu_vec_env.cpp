@@ -117,6 +117,9 @@ static void test_invalid_action() {
   for (auto [kind, bad] : {std::pair<int, int>{MGYM_CARTPOLE_V1, 2}, {MGYM_MOUNTAIN_CAR_V0, 3}}) {
     auto env = mgym::GpuVecEnv::builder(kind, 4).validate_actions(true).build();
     env.reset();
+    std::vector<float> before, after;
+    std::vector<uint32_t> steps0, steps1, sbt;
+    env.get_state(before, steps0, sbt);
     bool threw = false;
     try {
       env.step_host(std::vector<uint8_t>{0, 1, (uint8_t)bad, 0});
@@ -124,6 +127,9 @@ static void test_invalid_action() {
       threw = true;
     }
     CHECK(threw, "kind %d: action %d must be rejected", kind, bad);
+    // the reference asserts before any mutation (cartpole.rs:252): nothing was stepped
+    env.get_state(after, steps1, sbt);
+    CHECK(before == after && steps0 == steps1, "kind %d: the rejected batch must leave the handle untouched", kind);
     CHECK(!env.action_space_discrete().contains(bad) && env.action_space_discrete().contains(bad - 1), "Discrete::contains");
   }
   std::printf("ok   test_*_invalid_action\n");
